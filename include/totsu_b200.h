@@ -1,0 +1,176 @@
+/*
+ * totsu_b200.h — C ABI of libtotsu_b200.so, the B200 (sm_100a) linear-algebra / cone backend for
+ * Totsu's first-order conic solver.
+ *
+ * This is the boundary a Rust FFI crate `totsu_b200` (a sibling of `totsu_f64lapack` / `totsu_f32cuda`)
+ * binds: one entry point per function of the reference's plugin traits
+ *
+ *     LinAlg     solver_rust_conic/totsu_core/src/solver/linalg.rs:10-68
+ *     LinAlgEx   solver_rust_conic/totsu_core/src/linalg_ex.rs:7-66
+ *     SliceLike  solver_rust_conic/totsu_core/src/solver/slicelike.rs:9-70
+ *     Operator   solver_rust_conic/totsu_core/src/solver/operator.rs:11-156   (fused dense operator)
+ *     Cone       solver_rust_conic/totsu_core/src/solver/cone.rs:9-30         (batched product cone)
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, scalars by value; no C++/torch types.
+ *   - every function returns 0 (TB_OK) or a TB_ERR_* code; tb_last_error() gives the message.  The traits
+ *     have no error channel, so the Rust shim asserts on the status exactly like totsu_f32cuda does with
+ *     cuBLAS statuses (totsu_f32cuda/src/f32cuda.rs:38).
+ *   - `LinAlg` functions are associated functions without `self` (linalg.rs:22-67), so the backend state is a
+ *     process-global context bound to ONE device (one process per GPU); not re-entrant, single host thread.
+ *   - element type is chosen by the suffix: _f32 (type F = f32) or _f64 (type F = f64).
+ *   - vectors/matrices are "views" = (buffer handle, offset, length) in elements, the image of a Rust
+ *     sub-slice produced by SliceLike::split_ref/split_mut.  There is no CPU fallback anywhere.
+ */
+#ifndef TOTSU_B200_H
+#define TOTSU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t tb_handle;                 /* > 0 when valid */
+
+typedef struct tb_view {
+    tb_handle buf;                         /* root buffer */
+    size_t    off;                         /* offset in elements */
+    size_t    len;                         /* length in elements */
+} tb_view;
+
+enum { TB_OK = 0, TB_ERR_CUDA = 1, TB_ERR_ARG = 2, TB_ERR_STATE = 3, TB_ERR_NCCL = 4, TB_ERR_UNSUPPORTED = 5 };
+enum { TB_F32 = 0, TB_F64 = 1 };
+
+/* ---- lifecycle (role of totsu_f32cuda/src/cuda_mgr.rs:12-162) ------------------------------------------ */
+int         tb_init(int device);           /* device ordinal; -1 = $LOCAL_RANK or 0.  Idempotent. */
+int         tb_shutdown(void);
+const char* tb_last_error(void);
+int         tb_device_sync(void);
+int         tb_get_stream(void** cuda_stream_out);   /* the cudaStream_t every call is enqueued on (for event timing) */
+int         tb_sm_count(int* out);
+/* number of kernels this library has launched since tb_init (bench.py's gpu_launches claim) */
+int         tb_launch_count(uint64_t* out);
+/* CUDA-event timing of the dominant kernel (the streaming matvec) on the library's own stream, for bench.py's
+ * roofline: enable, run, then read (launch count, summed kernel milliseconds, summed algorithmic bytes). */
+int         tb_prof_enable(int on);
+int         tb_prof_read(uint64_t* launches, double* total_ms, double* total_bytes);
+/* tuning knob for tests: 0 = auto, 1 = force the generic (LDG) matvec, 2 = force the TMA matvec where legal */
+int         tb_set_gemv_path(int mode);
+
+/* ---- buffers: the SliceLike role (slicelike.rs:23-69; totsu_f32cuda/src/f32cuda_slice.rs:215-309) ------- */
+/* SliceLike::new_ref / new_mut: wrap caller-owned host memory with a device mirror.  The host slice stays
+ * the caller's; it is made coherent on tb_host_ref/tb_host_mut and on tb_buf_release (slicelike.rs:18-19). */
+int tb_buf_wrap(int dtype, void* host, size_t len, int host_is_mut, tb_handle* out);
+/* device-only buffer (no host mirror), zero-filled: used for matrices generated in HBM */
+int tb_buf_alloc(int dtype, size_t len, tb_handle* out);
+/* SliceLike::drop of a root slice: flush device-newer ranges to the host slice (if mutable) and free */
+int tb_buf_release(tb_handle buf);
+int tb_buf_len(tb_handle buf, size_t* out);
+/* SliceLike::get_ref / get_mut: make the host range current (D2H of device-newer sub-ranges);
+ * get_mut additionally marks the range host-newer so the next device use re-uploads it */
+int tb_host_ref(tb_view v);
+int tb_host_mut(tb_view v);
+/* SliceLike::get / set (slicelike.rs:54-69) without the two nested splits */
+int tb_get1_f32(tb_view v, size_t idx, float* out);
+int tb_get1_f64(tb_view v, size_t idx, double* out);
+int tb_set1_f32(tb_view v, size_t idx, float val);
+int tb_set1_f64(tb_view v, size_t idx, double val);
+/* explicit copies between caller memory and the device copy of a view (tests, device-only buffers) */
+int tb_upload(tb_view v, const void* src);
+int tb_download(tb_view v, void* dst);
+
+/* ---- LinAlg (linalg.rs:22-67; CPU twin totsu_f64lapack/src/f64lapack.rs:20-73) -------------------------- */
+int tb_norm_f32(tb_view x, float* out);                                   /* linalg.rs:27  dnrm2  */
+int tb_norm_f64(tb_view x, double* out);
+int tb_copy_f32(tb_view x, tb_view y);                                    /* linalg.rs:33  dcopy  */
+int tb_copy_f64(tb_view x, tb_view y);
+int tb_scale_f32(float alpha, tb_view x);                                 /* linalg.rs:39  dscal; alpha==0 is a zero-fill */
+int tb_scale_f64(double alpha, tb_view x);
+int tb_add_f32(float alpha, tb_view x, tb_view y);                        /* linalg.rs:46  daxpy  */
+int tb_add_f64(double alpha, tb_view x, tb_view y);
+int tb_adds_f32(float s, tb_view y);                                      /* linalg.rs:52  daxpy incx=0 */
+int tb_adds_f64(double s, tb_view y);
+int tb_abssum_f32(tb_view x, size_t incx, float* out);                    /* linalg.rs:58  dasum over ceil(len/incx) */
+int tb_abssum_f64(tb_view x, size_t incx, double* out);
+int tb_transform_di_f32(float alpha, tb_view mat, tb_view x, float beta, tb_view y);   /* linalg.rs:67  dsbmv k=0 */
+int tb_transform_di_f64(double alpha, tb_view mat, tb_view x, double beta, tb_view y);
+
+/* ---- LinAlgEx (linalg_ex.rs:23-65; CPU twin f64lapack.rs:120-191) --------------------------------------- */
+/* y = alpha*G*x + beta*y  or  alpha*G^T*x + beta*y; G column-major n_row x n_col, lda = n_row (linalg_ex.rs:23) */
+int tb_transform_ge_f32(int transpose, size_t n_row, size_t n_col, float alpha, tb_view mat, tb_view x, float beta, tb_view y);
+int tb_transform_ge_f64(int transpose, size_t n_row, size_t n_col, double alpha, tb_view mat, tb_view x, double beta, tb_view y);
+/* y = alpha*S*x + beta*y; S symmetric, upper triangle packed by columns (linalg_ex.rs:37) */
+int tb_transform_sp_f32(size_t n, float alpha, tb_view mat, tb_view x, float beta, tb_view y);
+int tb_transform_sp_f64(size_t n, double alpha, tb_view mat, tb_view x, double beta, tb_view y);
+/* linalg_ex.rs:43 */
+size_t tb_map_eig_worklen(size_t n);
+/* linalg_ex.rs:64 map_eig, split around the host closure `map: Fn(F)->Option<F>`:
+ *   begin : unpack `mat` (optionally scaling the diagonal), eigendecompose on the device, return all n
+ *           eigenvalues in `host_eigs` (ascending order is NOT guaranteed);
+ *   (host applies the closure to the eigenvalues in (0, +inf] like dsyevr(range=V, vl=0) does, f64lapack.rs:86-107)
+ *   finish: mat := sum_i keep[i] ? new_eigs[i] * z_i z_i^T : 0, diagonal unscaled, repacked. */
+int tb_map_eig_begin_f32(tb_view mat, int has_scale, float scale_diag, float eps_zero, tb_view work, float* host_eigs);
+int tb_map_eig_begin_f64(tb_view mat, int has_scale, double scale_diag, double eps_zero, tb_view work, double* host_eigs);
+int tb_map_eig_finish_f32(tb_view mat, int has_scale, float scale_diag, tb_view work, const float* new_eigs, const uint8_t* keep);
+int tb_map_eig_finish_f64(tb_view mat, int has_scale, double scale_diag, tb_view work, const double* new_eigs, const uint8_t* keep);
+/* ConePSD::proj fast path (cone_psd.rs:56-79): the closure `e > 0 ? Some(e) : None` applied on the device */
+int tb_proj_psd_f32(tb_view x, float eps_zero, tb_view work);
+int tb_proj_psd_f64(tb_view x, double eps_zero, tb_view work);
+
+/* ---- fused device-resident Operator (operator.rs:11-156) for one stacked dense A ------------------------ */
+/* `mat` is column-major n_row x n_col (lda = n_row): the rows THIS rank owns.  With tb_dist_init'ed world
+ * size G > 1 the operator is row-sharded: rows [row_offset, row_offset+n_row) of an n_row_total x n_col A;
+ * op() all-gathers the y slices, trans_op() all-reduces the partial sums (north_star). */
+int tb_denseop_create(int dtype, tb_view mat, size_t n_row, size_t n_col, size_t row_offset, size_t n_row_total, tb_handle* out);
+int tb_denseop_destroy(tb_handle op);
+/* Operator::op (transpose=0) / trans_op (transpose=1); x, y are full-length (replicated) vectors */
+int tb_denseop_apply_f32(tb_handle op, int transpose, float alpha, tb_view x, float beta, tb_view y);
+int tb_denseop_apply_f64(tb_handle op, int transpose, double alpha, tb_view x, double beta, tb_view y);
+/* one pass over A for an op / trans_op pair that reads different inputs and writes different outputs:
+ *   y_n = alpha_n*A*x_n + beta_n*y_n   and   y_t = alpha_t*A^T*x_t + beta_t*y_t   */
+int tb_denseop_apply_pair_f32(tb_handle op, float alpha_n, tb_view x_n, float beta_n, tb_view y_n,
+                              float alpha_t, tb_view x_t, float beta_t, tb_view y_t);
+int tb_denseop_apply_pair_f64(tb_handle op, double alpha_n, tb_view x_n, double beta_n, tb_view y_n,
+                              double alpha_t, tb_view x_t, double beta_t, tb_view y_t);
+/* Operator::absadd_cols (tau[c] += sum_r |A[r,c]|) and absadd_rows (sigma[r] += sum_c |A[r,c]|) */
+int tb_denseop_absadd_cols_f32(tb_handle op, tb_view tau);
+int tb_denseop_absadd_cols_f64(tb_handle op, tb_view tau);
+int tb_denseop_absadd_rows_f32(tb_handle op, tb_view sigma);
+int tb_denseop_absadd_rows_f64(tb_handle op, tb_view sigma);
+
+/* ---- batched product Cone (cone.rs:9-30; cone_{zero,rpos,soc,rotsoc}.rs) -------------------------------- */
+enum { TB_CONE_ZERO = 0, TB_CONE_RPOS = 1, TB_CONE_SOC = 2, TB_CONE_ROTSOC = 3, TB_CONE_PSD = 4 };
+typedef struct tb_cone_block { int32_t type; int32_t reserved; uint64_t len; } tb_cone_block;
+/* blocks are laid out back to back over the m-vector, like ProbSOCPCone (socp.rs:296-313) */
+int tb_cone_create(const tb_cone_block* blocks, size_t n_blocks, tb_handle* out);
+int tb_cone_destroy(tb_handle cone);
+/* Cone::proj for the whole product cone in one launch (+ one eigensolve per PSD block, using psd_work) */
+int tb_cone_proj_f32(tb_handle cone, int dual_cone, tb_view x, float eps_zero, tb_view psd_work);
+int tb_cone_proj_f64(tb_handle cone, int dual_cone, tb_view x, double eps_zero, tb_view psd_work);
+/* Cone::product_group with the solver's `group` closure (min over each block of size>1; solver.rs:509-523) */
+int tb_cone_group_min_f32(tb_handle cone, tb_view dp_tau);
+int tb_cone_group_min_f64(tb_handle cone, tb_view dp_tau);
+
+/* ---- vector helpers used by the solver's host loops (solver.rs:501-506, 551-552, 566-567) --------------- */
+/* x[i] = 1 / max(x[i], eps)  — calc_precond's two host loops over get_mut() */
+int tb_recip_clamp_f32(float eps, tb_view x);
+int tb_recip_clamp_f64(double eps, tb_view x);
+
+/* ---- synthetic instances (bench / tests): counter-based generator keyed (seed, global row, col) --------- */
+/* mat (column-major n_row x n_col, lda = n_row) := scale * (2*u(seed,row_offset+r,c) - 1), u in [0,1) with 24 bits */
+int tb_fill_uniform_f32(tb_view mat, size_t n_row, size_t n_col, size_t row_offset, uint64_t seed, float scale);
+int tb_fill_uniform_f64(tb_view mat, size_t n_row, size_t n_col, size_t row_offset, uint64_t seed, double scale);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink 5 / NVSwitch -------------------------------------- */
+#define TB_NCCL_ID_BYTES 128
+int tb_dist_unique_id(void* id_out /* TB_NCCL_ID_BYTES */);   /* rank 0, then broadcast by the launcher */
+int tb_dist_init(int rank, int world, const void* id);
+int tb_dist_finalize(void);
+int tb_dist_info(int* rank, int* world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOTSU_B200_H */

@@ -1,0 +1,160 @@
+"""GPU parity: batched product-cone projection (tb_cone_*), LinAlgEx::map_eig and the ConePSD projection,
+through the C ABI, against the oracle's cones (oracle/totsu_oracle.py = cone_*.rs / f64lapack.rs:78-255)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from helpers import O, capi, rel_linf, oracle_cone, svec, ZERO, RPOS, SOC, ROTSOC, PSD
+
+pytestmark = pytest.mark.gpu
+DTYPES = [np.float32, np.float64]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    capi.init(0)
+    yield
+
+
+def _cone(blocks):
+    blk = (capi.ConeBlock * len(blocks))(*[capi.ConeBlock(t, 0, ln) for t, ln in blocks])
+    h = C.c_int64()
+    capi.check(capi.lib().tb_cone_create(blk, len(blocks), C.byref(h)))
+    return h.value
+
+
+def _psd_worklen(blocks):
+    w = 0
+    for t, ln in blocks:
+        if t == PSD:
+            k = int((math.sqrt(8 * ln + 1) - 1) / 2 + 0.5)
+            w = max(w, 2 * k * k + k)
+    return w
+
+
+CASES = [
+    [(SOC, 64)] * 40 + [(ZERO, 5)],
+    [(ROTSOC, 10), (RPOS, 20), (ZERO, 4), (SOC, 1), (ROTSOC, 1), (SOC, 2), (ROTSOC, 2), (SOC, 0), (RPOS, 0)],
+    [(RPOS, 10000), (ZERO, 333)],
+    [(ROTSOC, 8194), (RPOS, 500), (ZERO, 100)],
+    [(SOC, 5000), (SOC, 3), (SOC, 2049)],
+    [(PSD, 3), (SOC, 5), (PSD, 55), (ZERO, 2)],
+]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("dual", [False, True])
+def test_product_cone_proj(dt, case, dual):
+    blocks = CASES[case]
+    m = sum(l for _, l in blocks)
+    rng = np.random.default_rng(case)
+    tol = 5e-6 if dt == np.float32 else 1e-12
+    # three regimes per SOC block: inside, in the polar (-> 0), and the generic case
+    for trial in range(3):
+        x = rng.standard_normal(m).astype(dt)
+        o = 0
+        for t, ln in blocks:
+            if t in (SOC, ROTSOC) and ln > 1 and trial < 2:
+                if t == SOC:
+                    x[o] = (1 if trial == 0 else -1) * (np.linalg.norm(x[o + 1:o + ln]) * 2 + 1)
+                else:
+                    big = np.linalg.norm(x[o + 2:o + ln]) * 2 + 1
+                    x[o] = x[o + 1] = (1 if trial == 0 else -1) * big
+            o += ln
+        want = x.astype(np.float64).copy()
+        oracle_cone(blocks).proj(dual, want)
+        got = x.copy()
+        h = _cone(blocks)
+        xb = capi.Buf(got)
+        wl = _psd_worklen(blocks)
+        wb = capi.Buf(np.zeros(max(wl, 1), dtype=dt))
+        capi.check(capi.fn("tb_cone_proj", dt)(h, 1 if dual else 0, xb.view(), 1e-12, wb.view() if wl else capi.View(0, 0, 0)))
+        xb.release(); wb.release()
+        capi.check(capi.lib().tb_cone_destroy(h))
+        has_psd = any(t == PSD for t, _ in blocks)
+        assert rel_linf(got, want) <= (tol * (50 if has_psd else 1)), (case, trial)
+        if trial == 0 and not has_psd:
+            # points inside a self-dual cone are fixed points (up to the rotation round trip for RotSOC)
+            o = 0
+            for t, ln in blocks:
+                if t == SOC and ln > 1:
+                    assert np.array_equal(got[o:o + ln], x[o:o + ln])
+                o += ln
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_product_group_min(dt):
+    blocks = CASES[1] + [(SOC, 3000), (PSD, 6)]
+    m = sum(l for _, l in blocks)
+    rng = np.random.default_rng(0)
+    t = (np.abs(rng.standard_normal(m)) + 0.1).astype(dt)
+    want = t.astype(np.float64).copy()
+
+    def group(g):
+        if g.size > 0:
+            g[...] = g.min()
+    oracle_cone(blocks).product_group(want, group)
+    h = _cone(blocks)
+    tb = capi.Buf(t)
+    capi.check(capi.fn("tb_cone_group_min", dt)(h, tb.view()))
+    tb.release()
+    capi.check(capi.lib().tb_cone_destroy(h))
+    assert np.array_equal(t.astype(np.float64), want.astype(dt).astype(np.float64))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_cone_psd_unit(dt):
+    """totsu_core/src/cone_psd.rs:89-110: proj of diag(5,-5) -> diag(5,0)."""
+    x = np.array([5., 0., -5.], dtype=dt)
+    xb, wb = capi.Buf(x), capi.Buf(np.zeros(10, dtype=dt))
+    capi.check(capi.fn("tb_proj_psd", dt)(xb.view(), 1e-12, wb.view()))
+    xb.release(); wb.release()
+    assert np.allclose(x, [5., 0., 0.], atol=1e-6)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 16, 33, 64, 129])
+def test_proj_psd_vs_oracle(dt, k):
+    rng = np.random.default_rng(k)
+    g = rng.standard_normal((k, k))
+    x = svec((g + g.T) / 2).astype(dt)
+    want = x.astype(np.float64).copy()
+    O.ConePSD(np.zeros(O.ConePSD.query_worklen(x.size)), 1e-12).proj(False, want)
+    xb, wb = capi.Buf(x), capi.Buf(np.zeros(2 * k * k + k, dtype=dt))
+    capi.check(capi.fn("tb_proj_psd", dt)(xb.view(), 1e-12, wb.view()))
+    xb.release(); wb.release()
+    tol = 2e-5 if dt == np.float32 else 1e-11
+    assert np.abs(x - want).max() <= tol * max(1.0, np.abs(want).max()), k
+    # idempotence and PSD-ness of the result
+    again = x.copy()
+    xb, wb = capi.Buf(again), capi.Buf(np.zeros(2 * k * k + k, dtype=dt))
+    capi.check(capi.fn("tb_proj_psd", dt)(xb.view(), 1e-12, wb.view()))
+    xb.release(); wb.release()
+    assert np.abs(again - x).max() <= 5 * tol * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("k", [2, 5, 40])
+def test_map_eig_sqrt_closure(dt, k):
+    """MatBuild::set_sqrt (matbuild/mod.rs:220-241): map_eig with scale_diag=None and e -> sqrt(e)."""
+    rng = np.random.default_rng(k)
+    g = rng.standard_normal((k, k + 2))
+    p = g @ g.T / k
+    packed = np.array([p[r, c] for c in range(k) for r in range(c + 1)], dtype=dt)
+    want = packed.astype(np.float64).copy()
+    O.F64LAPACK.map_eig(want, None, 1e-12, np.zeros(O.F64LAPACK.map_eig_worklen(k)), lambda e: math.sqrt(e) if e > 0 else None)
+    F = C.c_float if dt == np.float32 else C.c_double
+    mb, wb = capi.Buf(packed), capi.Buf(np.zeros(2 * k * k + k, dtype=dt))
+    eigs = (F * k)()
+    capi.check(capi.fn("tb_map_eig_begin", dt)(mb.view(), 0, 1.0, 1e-12, wb.view(), eigs))
+    ev = np.array(list(eigs), dtype=np.float64)
+    ref_ev = np.linalg.eigvalsh(p)
+    assert np.abs(np.sort(ev) - ref_ev).max() <= (3e-5 if dt == np.float32 else 1e-11) * max(1.0, ref_ev.max())
+    keep = (C.c_uint8 * k)(*[1 if e > 0 else 0 for e in ev])
+    new = (F * k)(*[math.sqrt(e) if e > 0 else 0.0 for e in ev])
+    capi.check(capi.fn("tb_map_eig_finish", dt)(mb.view(), 0, 1.0, wb.view(), new, keep))
+    mb.release(); wb.release()
+    assert np.abs(packed - want).max() <= (2e-3 if dt == np.float32 else 1e-10) * max(1.0, np.abs(want).max())

@@ -1,0 +1,199 @@
+"""GPU parity of the whole hot path: the C++ mirror of `Solver::solve` driving the B200 backend through the C ABI,
+against (a) the reference's own known answers / golden trace and (b) the oracle's iterates on seeded synthetic
+instances, on both the stock path (MatOp + stock cones, one backend call per trait call) and the fused path
+(DenseOp + ProductCone).  Mirrors totsu_core/tests/solver.rs and totsu/tests/{lp,qp,qcqp,socp,sdp}.rs."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from helpers import capi, ZERO, RPOS, SOC, ROTSOC, PSD
+from totsu_b200 import host
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    capi.init(0)
+    yield
+
+
+def _sym(rows):
+    """row-major full symmetric -> packed upper by columns (MatBuild::set_iter_rowmaj on a SymPack)."""
+    a = np.array(rows, dtype=np.float64)
+    k = a.shape[0]
+    return np.array([a[r, c] for c in range(k) for r in range(c + 1)])
+
+
+# ---- golden trace ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [False, True])
+def test_golden_trace_cortex_m_lp_f64(fused):
+    """examples/nostd_cortex-m/log_qemu.txt:7-25 on the device in f64: same iteration count, residuals equal to
+    the 3 printed digits up to the last-digit rounding of a different summation order, solution to 1e-9."""
+    c, a, b = [-1., 0.], np.array([[4., -1.], [-1., 4.], [-1., -1.]]), [6., 6., 1.]
+    abuf, av = H.device_matrix(np.asfortranarray(a))
+    s = host.Session.dense(np.float64, av, 3, 2, c, b, [(RPOS, 3)], fused_op=fused, fused_cone=fused)
+    assert s.begin(max_iter=100_000, log_period=10) == "None"
+    st, tr = s.run(trace_cap=64, only_logged=True)
+    s.end()
+    x, _ = s.solution()
+    s.close(); abuf.release()
+    assert st == "None"
+    want = [l.strip() for l in open(os.path.join(GOLDEN, "cortex_m_lp_trace.txt")) if l.strip() and not l.startswith("#")]
+    got = host.log_lines(tr)
+    assert len(got) == len(want) and got[-1].split(":")[0] == "159"
+    for g, w in zip(got, want):
+        gi, gv = g.split(": pri_dual_gap "); wi, wv = w.split(": pri_dual_gap ")
+        assert gi == wi
+        for a_, b_ in zip(gv.split(), wv.split()):
+            fa, fb = float(a_), float(b_)
+            assert abs(fa - fb) <= 0.011 * max(abs(fb), 1e-300) or (fa == fb), (g, w)
+    assert np.allclose(x, [1.9999994251590176, 2.0000004472430635], atol=1e-9)
+
+
+# ---- reference known answers (tolerance 1e-3, the reference's own) -----------------------------------------
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-6), (np.float32, 1e-4)])
+def test_backend_conformance_sdp(dt, eps):
+    """totsu_f32cuda/tests/solver.rs:14-55 == totsu_f64lapack/tests/solver.rs:15-56: raw MatOp + ConePSD, x = -2."""
+    for fused in (False, True):
+        a = np.array([[0.], [-1. * 1.41421356], [-3.]])
+        abuf, av = H.device_matrix(np.asfortranarray(a.astype(dt)))
+        s = host.Session.dense(dt, av, 3, 1, [1.], [1., 0. * 1.41421356, 10.], [(PSD, 3)], fused_op=fused, fused_cone=fused)
+        st, x, _ = s.solve(max_iter=100_000, eps_acc=eps)
+        s.close(); abuf.release()
+        assert st == "None" and abs(x[0] - (-2.0)) <= 1e-3
+
+
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-6), (np.float32, 1e-4)])
+def test_lp_infeasible_unbounded(dt, eps):
+    """totsu/tests/lp.rs:12-45 (Infeasible) and :49-82 (Unbounded) through ProbLP."""
+    s = host.Session.lp(dt, [1.], [[1.], [-1.]], [-5., -10.])
+    st, _, _ = s.solve(max_iter=100_000, eps_acc=eps, eps_inf=eps)
+    s.close()
+    assert st == "Infeasible"
+    s = host.Session.lp(dt, [1.], [[1.], [1.]], [5., 10.])
+    st, _, _ = s.solve(max_iter=100_000, eps_acc=eps, eps_inf=eps)
+    s.close()
+    assert st == "Unbounded"
+
+
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-6), (np.float32, 1e-4)])
+def test_qp1(dt, eps):
+    """totsu/tests/qp.rs:13-49 and the crate doc-test (totsu_f32cuda/src/lib.rs:31-76): x = [2, 0]."""
+    s = host.Session.qp(dt, _sym([[1., 0.], [0., 1.]]), [1., 2.], [[-0.5, -1. / 3.]], [-1.], np.zeros((0, 2)), [], 1e-12)
+    st, x, _ = s.solve(max_iter=100_000, eps_acc=eps)
+    s.close()
+    assert st == "None" and np.allclose(x[0:2], [2., 0.], atol=1e-3)
+
+
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-6), (np.float32, 1e-4)])
+def test_qcqp1(dt, eps):
+    """totsu/tests/qcqp.rs:13-48: x = [5, 4]."""
+    syms = [_sym([[1., 0.], [0., 1.]]), _sym([[0., 0.], [0., 0.]])]
+    s = host.Session.qcqp(dt, syms, [[-5., -4.], [-0.5, -1. / 3.]], [0., 1.], np.zeros((0, 2)), [], 1e-12)
+    st, x, _ = s.solve(max_iter=100_000, eps_acc=eps)
+    s.close()
+    assert st == "None" and np.allclose(x[0:2], [5., 4.], atol=1e-3)
+
+
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-6), (np.float32, 1e-4)])
+def test_socp1_socp2(dt, eps):
+    """totsu/tests/socp.rs:13-47 (x = [-1,-1]) and :51-94 (x = [2,0], first G block has 0 rows)."""
+    s = host.Session.socp(dt, [1., 1.], [np.eye(2)], [[0., 0.]], [[0., 0.]], [math.sqrt(2.)])
+    st, x, _ = s.solve(eps_acc=eps)
+    s.close()
+    assert st == "None" and np.allclose(x, [-1., -1.], atol=1e-3)
+    s = host.Session.socp(dt, [0., 1.], [np.zeros((0, 2)), np.array([[-1., 0.]])], [[], [2.]], [[0., -1.], [0., 1.]], [50., 0.])
+    st, x, _ = s.solve(max_iter=100_000, eps_acc=eps)
+    s.close()
+    assert st == "None" and np.allclose(x, [2., 0.], atol=1e-3)
+
+
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-6), (np.float32, 1e-4)])
+def test_sdp1(dt, eps):
+    """totsu/tests/sdp.rs:13-51: x = [3, 4]."""
+    syms = [_sym([[-1., 0.], [0., 0.]]), _sym([[0., 0.], [0., -1.]]), _sym([[3., 0.], [0., 4.]])]
+    s = host.Session.sdp(dt, [1., 1.], syms, np.zeros((0, 2)), [], 1e-12)
+    st, x, _ = s.solve(max_iter=100_000, eps_acc=eps)
+    s.close()
+    assert st == "None" and np.allclose(x, [3., 4.], atol=1e-3)
+
+
+# ---- synthetic parity vs the oracle's iterates -------------------------------------------------------------
+SYN = {
+    "socp": (lambda: ([(SOC, 16)] * 24 + [(ZERO, 16)], 96)),
+    "lp": (lambda: ([(RPOS, 300), (ZERO, 20)], 120)),
+    "qp_like": (lambda: ([(ROTSOC, 66), (RPOS, 64), (ZERO, 10)], 65)),
+    "sdp_like": (lambda: ([(PSD, 36), (RPOS, 10), (ZERO, 3)], 20)),
+    "stream": (lambda: ([(SOC, 64)] * 32 + [(RPOS, 512)], 1024)),      # 2560 x 1024: large enough for the TMA kernel
+}
+
+
+@pytest.mark.parametrize("name", list(SYN.keys()))
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_iterates_match_oracle(name, dt):
+    blocks, n = SYN[name]()
+    m = sum(l for _, l in blocks)
+    a, b, c = H.make_instance(m, n, blocks, seed=sorted(SYN.keys()).index(name) + 1, dtype=dt)
+    ks = [1, 10, 100]
+    snaps, trace = H.oracle_iterates(a, b, c, blocks, ks)
+    # stated tolerances: relative l_inf of x_hat / y_hat vs the f64 oracle
+    tol = {np.float64: {1: 1e-12, 10: 1e-11, 100: 1e-9}, np.float32: {1: 5e-6, 10: 5e-5, 100: 1e-4}}[dt]
+    if name == "sdp_like":
+        tol = {k: v * (100 if dt == np.float32 else 1e4) for k, v in tol.items()}      # eigensolver conditioning
+    abuf, av = H.device_matrix(a)
+    results = {}
+    for fused in (False, True):
+        s = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=fused, fused_cone=fused)
+        assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=fused) == "None"
+        done_k = 0
+        for k in ks:
+            s.step(k - done_k)
+            done_k = k
+            xh, yh = s.xy()
+            ex, ey = H.rel_linf(xh, snaps[k][0]), H.rel_linf(yh, snaps[k][1])
+            assert ex <= tol[k] and ey <= tol[k], (name, dt, fused, k, ex, ey)
+            # residual triple to 2 significant digits (solver.rs:391) at f32, tighter at f64
+            it = s.last
+            ref = trace[k - 1]
+            rt = 5e-3 if dt == np.float32 else 1e-8
+            if name == "sdp_like":
+                rt *= 20
+            for got, want in zip((it.c0, it.c1, it.c2), ref[1:]):
+                assert abs(got - want) <= rt * max(abs(want), 1e-3), (name, dt, fused, k, got, want)
+            results[(fused, k)] = (xh, yh)
+        s.close()
+    abuf.release()
+    # stock and fused paths agree with each other at least as well as with the oracle
+    for k in ks:
+        assert H.rel_linf(results[(True, k)][0], results[(False, k)][0]) <= 2 * tol[k]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_front_end_socp_matches_fused_dense(dt):
+    """ProbSOCP (per-block MatOps, socp.rs:83-124) and the stacked DenseOp produce the same iterates: the row order
+    [-c_i^T; -G_i] ... of socp.rs:359-366 is what the fused operator stacks."""
+    rng = np.random.default_rng(5)
+    n, nblk, ni = 12, 5, 4
+    f = rng.standard_normal(n)
+    gs = [rng.standard_normal((ni, n)) for _ in range(nblk)]
+    hs = [rng.standard_normal(ni) for _ in range(nblk)]
+    cs = [rng.standard_normal(n) * 0.1 for _ in range(nblk)]
+    ds = [float(np.linalg.norm(h) + 1.0) for h in hs]
+    cast = lambda v: np.asarray(v, dtype=dt)
+    s1 = host.Session.socp(dt, cast(f), [cast(g) for g in gs], [cast(h) for h in hs], [cast(c) for c in cs], cast(ds))
+    a = np.vstack([np.vstack([-cast(c)[None, :], -cast(g)]) for c, g in zip(cs, gs)])
+    b = np.concatenate([np.concatenate([[cast(d)], cast(h)]) for d, h in zip(ds, hs)])
+    abuf, av = H.device_matrix(np.asfortranarray(a))
+    s2 = host.Session.dense(dt, av, a.shape[0], n, cast(f), b, [(SOC, 1 + ni)] * nblk)
+    for s in (s1, s2):
+        assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0) == "None"
+        s.step(50)
+    (x1, y1), (x2, y2) = s1.xy(), s2.xy()
+    s1.close(); s2.close(); abuf.release()
+    tol = 1e-10 if dt == np.float64 else 2e-4
+    assert H.rel_linf(x1, x2) <= tol and H.rel_linf(y1, y2) <= tol

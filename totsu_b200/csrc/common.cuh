@@ -1,0 +1,236 @@
+// Shared internals of libtotsu_b200.so: the process-global context, buffer table with host/device
+// coherence tracking, error plumbing and small device helpers.  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <algorithm>
+#include "../../include/totsu_b200.h"
+
+namespace tb {
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+[[noreturn]] inline void fail(int code, const std::string& m) { throw Error{code, m}; }
+
+#define TB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            ::tb::fail(TB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +    \
+                                        __FILE__ + ":" + std::to_string(__LINE__) + ")");          \
+    } while (0)
+
+#define TB_REQUIRE(cond, msg)                                                                      \
+    do {                                                                                           \
+        if (!(cond)) ::tb::fail(TB_ERR_ARG, std::string(msg) + " [" #cond "] (" + __FILE__ + ":" + \
+                                                std::to_string(__LINE__) + ")");                   \
+    } while (0)
+
+// Sorted set of disjoint half-open element ranges.  Replaces F32CUDASlice's per-split 3-state machine
+// (f32cuda_slice.rs:14-20,157-168): coherence is tracked per root buffer as "which ranges are newer on
+// the host" and "which are newer on the device", so splitting a slice costs nothing.
+class IntervalSet {
+public:
+    struct Iv { size_t a, b; };
+    bool empty() const { return v_.empty(); }
+    void clear() { v_.clear(); }
+    void add(size_t a, size_t b) {
+        if (a >= b) return;
+        std::vector<Iv> out;
+        out.reserve(v_.size() + 1);
+        size_t i = 0;
+        while (i < v_.size() && v_[i].b < a) out.push_back(v_[i++]);
+        while (i < v_.size() && v_[i].a <= b) { a = std::min(a, v_[i].a); b = std::max(b, v_[i].b); ++i; }
+        out.push_back({a, b});
+        while (i < v_.size()) out.push_back(v_[i++]);
+        v_.swap(out);
+    }
+    void sub(size_t a, size_t b) {
+        if (a >= b || v_.empty()) return;
+        std::vector<Iv> out;
+        out.reserve(v_.size() + 1);
+        for (const Iv& iv : v_) {
+            if (iv.b <= a || iv.a >= b) { out.push_back(iv); continue; }
+            if (iv.a < a) out.push_back({iv.a, a});
+            if (iv.b > b) out.push_back({b, iv.b});
+        }
+        v_.swap(out);
+    }
+    bool intersects(size_t a, size_t b) const {
+        for (const Iv& iv : v_) if (iv.a < b && a < iv.b) return true;
+        return false;
+    }
+    template <typename F> void for_each_in(size_t a, size_t b, F f) const {
+        for (const Iv& iv : v_) {
+            size_t lo = std::max(a, iv.a), hi = std::min(b, iv.b);
+            if (lo < hi) f(lo, hi);
+        }
+    }
+    const std::vector<Iv>& ivs() const { return v_; }
+private:
+    std::vector<Iv> v_;
+};
+
+struct Buffer {
+    bool alive = false;
+    int dtype = TB_F32;
+    size_t len = 0;
+    size_t esize = 4;
+    char* dev = nullptr;
+    char* host = nullptr;      // caller-owned mirror, may be null (device-only)
+    bool host_mut = false;
+    int small_slot = -1;       // >= 0: carved from the small-buffer slab, no cudaMalloc/cudaFree
+    IntervalSet host_newer;    // host copy is newer than device
+    IntervalSet dev_newer;     // device copy is newer than host
+};
+
+struct DenseOp;
+struct ConeSet;
+
+struct Context {
+    bool inited = false;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::vector<Buffer> bufs;            // handle = index + 1
+    std::vector<int64_t> free_ids;
+    // scratch for two-stage (deterministic) reductions / matvec partials
+    char* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // scalar mailbox: pinned host memory for D2H of reduction results / get1
+    double* mailbox_host = nullptr;
+    double* mailbox_dev = nullptr;       // device-side staging for reduction results
+    unsigned int* tickets = nullptr;     // "last block done" counters
+    // slab for tiny buffers (the solver wraps a 1-element slice every iteration: solver.rs:590-591)
+    char* small_slab = nullptr;
+    std::vector<int> small_free;
+    static constexpr size_t kSmallBytes = 256;
+    static constexpr int kSmallSlots = 1024;
+    uint64_t launches = 0;
+    int gemv_mode = 0;
+    // event-pair profiling of the streaming matvec
+    bool prof_on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pairs;   // recorded, not yet read
+    std::vector<cudaEvent_t> prof_pool;
+    uint64_t prof_launches = 0;
+    double prof_ms = 0.0, prof_bytes = 0.0;
+    std::vector<DenseOp*> denseops;
+    std::vector<ConeSet*> cones;
+    // distributed
+    int rank = 0, world = 1;
+    void* nccl_comm = nullptr;
+    std::string last_error;
+};
+
+Context& ctx();
+void require_init();
+
+Buffer& get_buf(tb_handle h);
+// Make [off, off+len) current on the device; if `write`, mark it device-newer.  Returns the device pointer
+// of element `off`.  `full_overwrite` skips the upload of host-newer data the kernel will overwrite anyway.
+char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite = false);
+void* scratch(size_t bytes);
+
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int id = TB_F32; };
+template <> struct DT<double> { static constexpr int id = TB_F64; };
+
+template <typename T> inline const T* rptr(const tb_view& v) { return reinterpret_cast<const T*>(dev_ptr(v, DT<T>::id, false)); }
+template <typename T> inline T* wptr(const tb_view& v, bool full_overwrite = false) { return reinterpret_cast<T*>(dev_ptr(v, DT<T>::id, true, full_overwrite)); }
+
+inline void count_launch(int n = 1) { ctx().launches += (uint64_t)n; }
+#define TB_LAUNCH_CHECK()                   \
+    do {                                    \
+        TB_CUDA(cudaGetLastError());        \
+        ::tb::count_launch();               \
+    } while (0)
+
+// API wrapper: translate internal exceptions to status codes.
+template <typename F> inline int api(F f) {
+    try {
+        f();
+        return TB_OK;
+    } catch (const Error& e) {
+        ctx().last_error = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        ctx().last_error = e.what();
+        return TB_ERR_STATE;
+    }
+}
+
+// ---- level-1 internals reused across translation units -------------------------------------------------
+template <typename T> void l1_scale(T alpha, T* x, size_t n);
+template <typename T> void l1_axpby(T alpha, const T* x, T beta, T* y, size_t n);   // y = alpha*x + beta*y (beta==0: y not read)
+template <typename T> void l1_copy(const T* x, T* y, size_t n);
+template <typename T> double l1_sumsq_sync(const T* x, size_t n);                   // returns sum of squares (double), syncs
+
+// ---- distributed internals ------------------------------------------------------------------------------
+void dist_allreduce_sum(void* buf, size_t count, int dtype);
+void dist_allgather_inplace(void* base, size_t count_per_rank, int dtype);   // rank r's slice lives at base + r*count
+
+// ---- eig internals (cone.cu calls into eig.cu for PSD blocks) -------------------------------------------
+template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len);
+
+}  // namespace tb
+
+// ---- device helpers -------------------------------------------------------------------------------------
+namespace tbd {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Deterministic block-wide sum; result valid in thread 0 (and broadcast through smem to all).
+// `red` must hold >= 32 doubles.  blockDim.x must be a multiple of 32.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < nw) ? red[lane] : 0.0;
+        r = warp_sum(r);
+        if (lane == 0) red[0] = r;
+    }
+    __syncthreads();
+    return red[0];
+}
+__device__ __forceinline__ double block_min(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_min(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        double r = (lane < nw) ? red[lane] : red[0];
+        r = warp_min(r);
+        if (lane == 0) red[0] = r;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+}  // namespace tbd

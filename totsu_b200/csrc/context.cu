@@ -1,0 +1,365 @@
+// Context, buffer table and host/device coherence: the SliceLike role of the backend
+// (reference: solver_rust_conic/totsu_core/src/solver/slicelike.rs:9-70; prior art being replaced:
+// totsu_f32cuda/src/f32cuda_slice.rs and cuda_mgr.rs).  B200-first redesign: one device allocation per root
+// slice, range-based dirty tracking instead of a per-split state machine + HashMap, a slab for the tiny
+// 1-element slices the solver wraps every iteration, and a pinned mailbox for host-visible scalars.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace tb {
+
+static Context g_ctx;
+Context& ctx() { return g_ctx; }
+
+void require_init() {
+    if (!g_ctx.inited) fail(TB_ERR_STATE, "tb_init has not been called");
+}
+
+Buffer& get_buf(tb_handle h) {
+    Context& c = ctx();
+    if (h <= 0 || (size_t)h > c.bufs.size() || !c.bufs[(size_t)h - 1].alive) fail(TB_ERR_ARG, "invalid buffer handle");
+    return c.bufs[(size_t)h - 1];
+}
+
+void* scratch(size_t bytes) {
+    Context& c = ctx();
+    if (bytes > c.scratch_bytes) {
+        // grow; the stream is drained first so no in-flight kernel still reads the old block
+        TB_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.scratch) TB_CUDA(cudaFree(c.scratch));
+        size_t nb = std::max(bytes, c.scratch_bytes * 2);
+        nb = (nb + 255) & ~size_t(255);
+        TB_CUDA(cudaMalloc(&c.scratch, nb));
+        c.scratch_bytes = nb;
+    }
+    return c.scratch;
+}
+
+// Tiny host->device updates travel as a kernel argument: fully asynchronous, no pageable-memory staging
+// (a cudaMemcpyAsync from pageable memory may synchronise the stream).
+struct SmallPayload { unsigned char b[Context::kSmallBytes]; };
+__global__ void poke_kernel(unsigned char* dst, SmallPayload p, unsigned int nbytes) {
+    for (unsigned int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = p.b[i];
+}
+
+char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite) {
+    Buffer& b = get_buf(v.buf);
+    if (b.dtype != dtype) fail(TB_ERR_ARG, "view element type does not match the function suffix");
+    if (v.off > b.len || v.len > b.len - v.off) fail(TB_ERR_ARG, "view out of range");
+    Context& c = ctx();
+    if (!b.host_newer.empty() && v.len > 0) {
+        if (!(write && full_overwrite)) {
+            b.host_newer.for_each_in(v.off, v.off + v.len, [&](size_t lo, size_t hi) {
+                size_t nb = (hi - lo) * b.esize;
+                if (nb <= Context::kSmallBytes) {
+                    SmallPayload p;
+                    std::memcpy(p.b, b.host + lo * b.esize, nb);
+                    poke_kernel<<<1, 64, 0, c.stream>>>((unsigned char*)(b.dev + lo * b.esize), p, (unsigned int)nb);
+                    TB_LAUNCH_CHECK();
+                } else {
+                    TB_CUDA(cudaMemcpyAsync(b.dev + lo * b.esize, b.host + lo * b.esize, nb, cudaMemcpyHostToDevice, c.stream));
+                }
+            });
+        }
+        b.host_newer.sub(v.off, v.off + v.len);
+    }
+    if (write && b.host && b.host_mut && v.len > 0) b.dev_newer.add(v.off, v.off + v.len);
+    return b.dev + v.off * b.esize;
+}
+
+static tb_handle new_handle() {
+    Context& c = ctx();
+    if (!c.free_ids.empty()) {
+        tb_handle h = c.free_ids.back();
+        c.free_ids.pop_back();
+        return h;
+    }
+    c.bufs.emplace_back();
+    return (tb_handle)c.bufs.size();
+}
+
+static void alloc_dev(Buffer& b) {
+    Context& c = ctx();
+    size_t bytes = b.len * b.esize;
+    if (bytes <= Context::kSmallBytes && !c.small_free.empty()) {
+        b.small_slot = c.small_free.back();
+        c.small_free.pop_back();
+        b.dev = c.small_slab + (size_t)b.small_slot * Context::kSmallBytes;
+    } else {
+        b.small_slot = -1;
+        TB_CUDA(cudaMalloc(&b.dev, std::max<size_t>(bytes, 16)));
+    }
+}
+
+static void host_sync_range(Buffer& b, size_t off, size_t len) {
+    Context& c = ctx();
+    bool any = false;
+    b.dev_newer.for_each_in(off, off + len, [&](size_t lo, size_t hi) {
+        TB_CUDA(cudaMemcpyAsync(b.host + lo * b.esize, b.dev + lo * b.esize, (hi - lo) * b.esize,
+                                cudaMemcpyDeviceToHost, c.stream));
+        any = true;
+    });
+    if (any) {
+        TB_CUDA(cudaStreamSynchronize(c.stream));
+        b.dev_newer.sub(off, off + len);
+    }
+}
+
+template <typename T> __global__ void set1_kernel(T* p, T v) { *p = v; }
+
+template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
+    require_init();
+    Buffer& b = get_buf(v.buf);
+    TB_REQUIRE(b.dtype == DT<T>::id, "dtype mismatch");
+    TB_REQUIRE(v.off <= b.len && v.len <= b.len - v.off && idx < v.len, "index out of range");
+    size_t i = v.off + idx;
+    Context& c = ctx();
+    if (b.host && !b.dev_newer.intersects(i, i + 1)) {   // host copy is current: no device round trip
+        *out = reinterpret_cast<const T*>(b.host)[i];
+        return;
+    }
+    TB_CUDA(cudaMemcpyAsync(c.mailbox_host, b.dev + i * b.esize, sizeof(T), cudaMemcpyDeviceToHost, c.stream));
+    TB_CUDA(cudaStreamSynchronize(c.stream));
+    *out = *reinterpret_cast<const T*>(c.mailbox_host);
+    if (b.host && b.host_mut) {      // like SliceLike::get -> get_ref on the 1-element split: host copy becomes current
+        reinterpret_cast<T*>(b.host)[i] = *out;
+        b.dev_newer.sub(i, i + 1);
+    }
+}
+
+template <typename T> static void set1(const tb_view& v, size_t idx, T val) {
+    require_init();
+    TB_REQUIRE(idx < v.len, "index out of range");
+    tb_view one{v.buf, v.off + idx, 1};
+    T* p = wptr<T>(one, true);
+    set1_kernel<T><<<1, 1, 0, ctx().stream>>>(p, val);
+    TB_LAUNCH_CHECK();
+    Buffer& b = get_buf(v.buf);
+    if (b.host && b.host_mut) {      // write-through: both copies agree, a following get() needs no device round trip
+        reinterpret_cast<T*>(b.host)[v.off + idx] = val;
+        b.dev_newer.sub(v.off + idx, v.off + idx + 1);
+    }
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int tb_init(int device) {
+    return api([&] {
+        Context& c = ctx();
+        if (c.inited) return;
+        if (device < 0) {
+            const char* lr = std::getenv("LOCAL_RANK");
+            device = lr ? std::atoi(lr) : 0;
+        }
+        int ndev = 0;
+        TB_CUDA(cudaGetDeviceCount(&ndev));
+        if (ndev <= 0) fail(TB_ERR_CUDA, "no CUDA device visible: totsu_b200 has no CPU fallback");
+        if (device >= ndev) fail(TB_ERR_ARG, "device ordinal out of range");
+        TB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        TB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) fail(TB_ERR_UNSUPPORTED, std::string("totsu_b200 is built for sm_100a (B200); found ") + prop.name);
+        c.device = device;
+        c.sm_count = prop.multiProcessorCount;
+        TB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        TB_CUDA(cudaHostAlloc(&c.mailbox_host, 64 * sizeof(double), cudaHostAllocDefault));
+        TB_CUDA(cudaMalloc(&c.mailbox_dev, 64 * sizeof(double)));
+        TB_CUDA(cudaMalloc(&c.tickets, 64 * sizeof(unsigned int)));
+        TB_CUDA(cudaMemset(c.tickets, 0, 64 * sizeof(unsigned int)));
+        TB_CUDA(cudaMalloc(&c.small_slab, Context::kSmallBytes * Context::kSmallSlots));
+        TB_CUDA(cudaMemset(c.small_slab, 0, Context::kSmallBytes * Context::kSmallSlots));
+        c.small_free.clear();
+        for (int i = Context::kSmallSlots - 1; i >= 0; --i) c.small_free.push_back(i);
+        c.scratch = nullptr;
+        c.scratch_bytes = 0;
+        (void)scratch(size_t(8) << 20);
+        c.launches = 0;
+        c.inited = true;
+    });
+}
+
+int tb_shutdown(void) {
+    return api([&] {
+        Context& c = ctx();
+        if (!c.inited) return;
+        cudaStreamSynchronize(c.stream);
+        for (Buffer& b : c.bufs)
+            if (b.alive && b.small_slot < 0 && b.dev) cudaFree(b.dev);
+        c.bufs.clear();
+        c.free_ids.clear();
+        if (c.scratch) cudaFree(c.scratch);
+        c.scratch = nullptr;
+        c.scratch_bytes = 0;
+        cudaFreeHost(c.mailbox_host);
+        cudaFree(c.mailbox_dev);
+        cudaFree(c.tickets);
+        cudaFree(c.small_slab);
+        cudaStreamDestroy(c.stream);
+        c.stream = nullptr;
+        c.inited = false;
+    });
+}
+
+const char* tb_last_error(void) { return ctx().last_error.c_str(); }
+
+int tb_device_sync(void) {
+    return api([&] {
+        require_init();
+        TB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+
+int tb_get_stream(void** out) {
+    return api([&] {
+        require_init();
+        *out = (void*)ctx().stream;
+    });
+}
+
+int tb_sm_count(int* out) {
+    return api([&] {
+        require_init();
+        *out = ctx().sm_count;
+    });
+}
+
+int tb_launch_count(uint64_t* out) {
+    return api([&] { *out = ctx().launches; });
+}
+
+int tb_set_gemv_path(int mode) {
+    return api([&] {
+        TB_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+        ctx().gemv_mode = mode;
+    });
+}
+
+int tb_buf_wrap(int dtype, void* host, size_t len, int host_is_mut, tb_handle* out) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(dtype == TB_F32 || dtype == TB_F64, "bad dtype");
+        TB_REQUIRE(host != nullptr || len == 0, "null host pointer");
+        tb_handle h = new_handle();
+        Buffer& b = ctx().bufs[(size_t)h - 1];
+        b = Buffer();
+        b.dtype = dtype;
+        b.esize = dtype == TB_F32 ? 4 : 8;
+        b.len = len;
+        b.host = (char*)host;
+        b.host_mut = host_is_mut != 0;
+        try {
+            alloc_dev(b);
+        } catch (...) {
+            ctx().free_ids.push_back(h);
+            throw;
+        }
+        b.alive = true;
+        if (len > 0) b.host_newer.add(0, len);   // uploaded on first device use (or right away for big read-only data)
+        if (!b.host_mut && len * b.esize >= (size_t(1) << 20)) {
+            tb_view v{h, 0, len};
+            (void)dev_ptr(v, dtype, false);       // matrices: upload now, like MatOp::new -> new_ref does (matop.rs:66-74)
+        }
+        *out = h;
+    });
+}
+
+int tb_buf_alloc(int dtype, size_t len, tb_handle* out) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(dtype == TB_F32 || dtype == TB_F64, "bad dtype");
+        tb_handle h = new_handle();
+        Buffer& b = ctx().bufs[(size_t)h - 1];
+        b = Buffer();
+        b.dtype = dtype;
+        b.esize = dtype == TB_F32 ? 4 : 8;
+        b.len = len;
+        try {
+            alloc_dev(b);
+        } catch (...) {
+            ctx().free_ids.push_back(h);
+            throw;
+        }
+        b.alive = true;
+        TB_CUDA(cudaMemsetAsync(b.dev, 0, std::max<size_t>(len * b.esize, 0), ctx().stream));
+        *out = h;
+    });
+}
+
+int tb_buf_release(tb_handle h) {
+    return api([&] {
+        require_init();
+        Buffer& b = get_buf(h);
+        Context& c = ctx();
+        if (b.host && b.host_mut) host_sync_range(b, 0, b.len);
+        if (b.small_slot >= 0) {
+            // slab slots are recycled without a device sync: every use is stream-ordered
+            c.small_free.push_back(b.small_slot);
+        } else if (b.dev) {
+            TB_CUDA(cudaStreamSynchronize(c.stream));
+            TB_CUDA(cudaFree(b.dev));
+        }
+        b = Buffer();
+        c.free_ids.push_back(h);
+    });
+}
+
+int tb_buf_len(tb_handle h, size_t* out) {
+    return api([&] {
+        require_init();
+        *out = get_buf(h).len;
+    });
+}
+
+int tb_host_ref(tb_view v) {
+    return api([&] {
+        require_init();
+        Buffer& b = get_buf(v.buf);
+        TB_REQUIRE(b.host != nullptr, "buffer has no host mirror");
+        TB_REQUIRE(v.off <= b.len && v.len <= b.len - v.off, "view out of range");
+        host_sync_range(b, v.off, v.len);
+    });
+}
+
+int tb_host_mut(tb_view v) {
+    return api([&] {
+        require_init();
+        Buffer& b = get_buf(v.buf);
+        TB_REQUIRE(b.host != nullptr && b.host_mut, "buffer has no mutable host mirror");
+        TB_REQUIRE(v.off <= b.len && v.len <= b.len - v.off, "view out of range");
+        host_sync_range(b, v.off, v.len);
+        b.host_newer.add(v.off, v.off + v.len);
+    });
+}
+
+int tb_get1_f32(tb_view v, size_t idx, float* out) { return api([&] { get1<float>(v, idx, out); }); }
+int tb_get1_f64(tb_view v, size_t idx, double* out) { return api([&] { get1<double>(v, idx, out); }); }
+int tb_set1_f32(tb_view v, size_t idx, float val) { return api([&] { set1<float>(v, idx, val); }); }
+int tb_set1_f64(tb_view v, size_t idx, double val) { return api([&] { set1<double>(v, idx, val); }); }
+
+int tb_upload(tb_view v, const void* src) {
+    return api([&] {
+        require_init();
+        Buffer& b = get_buf(v.buf);
+        char* d = dev_ptr(v, b.dtype, true, true);
+        if (v.len == 0) return;
+        TB_CUDA(cudaMemcpyAsync(d, src, v.len * b.esize, cudaMemcpyHostToDevice, ctx().stream));
+        TB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+
+int tb_download(tb_view v, void* dst) {
+    return api([&] {
+        require_init();
+        Buffer& b = get_buf(v.buf);
+        char* d = dev_ptr(v, b.dtype, false);
+        if (v.len == 0) return;
+        TB_CUDA(cudaMemcpyAsync(dst, d, v.len * b.esize, cudaMemcpyDeviceToHost, ctx().stream));
+        TB_CUDA(cudaStreamSynchronize(ctx().stream));
+    });
+}
+
+}  // extern "C"

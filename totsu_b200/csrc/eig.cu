@@ -1,0 +1,294 @@
+// LinAlgEx::map_eig (totsu_core/src/linalg_ex.rs:43-65) and the ConePSD projection built on it
+// (totsu_core/src/cone_psd.rs:56-79).  CPU twin: totsu_f64lapack/src/f64lapack.rs:78-108 (dsyevr V/V/U
+// (0,+inf] + a dsyr loop), :172-190 (map_eig), :195-255 (vec_to_mat / mat_to_vec).  Superseded GPU path:
+// totsu_f32cuda/src/f32cuda.rs:218-370 (cusolverDnSsyevdx + up to k cublasSsyr launches + 2k cublasScopy).
+//
+// Work layout (2k^2 + k elements, same as the reference): a[k*k] | w[k] | z[k*k], all column-major.
+//
+//   1. unpack: packed upper triangle -> full symmetric a, diagonal scaled (the sqrt(2) convention, cone_psd.rs:18)
+//   2. eigendecomposition by parallel one-sided Jacobi on B = a + s*I, s >= ||a||_F >= -lambda_min, so B is
+//      symmetric positive semi-definite and its singular pairs ARE its eigenpairs: rotations orthogonalise the
+//      columns of G (initially B) while V accumulates them; at convergence G = V*diag(sigma), lambda = sigma - s.
+//      k/2 disjoint column pairs per step (round-robin tournament), one CTA per pair, k-1 steps per sweep.
+//   3. reconstruct: a := sum_i coef_i z_i z_i^T as a tiled GEMM (Z*diag(coef))*Z^T over the upper tiles
+//   4. pack: upper triangle back into the vector, diagonal unscaled.
+// Round 1 keeps the GEMM on the FP32/FP64 pipes; moving step 3 (and a blocked two-sided variant of step 2)
+// onto tcgen05 is tracked in DESIGN.md.
+#include "common.cuh"
+#include <cmath>
+
+namespace tb {
+
+constexpr int EG_THREADS = 128;
+
+template <typename T>
+__global__ void unpack_kernel(const T* __restrict__ x, size_t k, int has_scale, T scale, T* __restrict__ a) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    size_t r = idx % k, c = idx / k;
+    size_t rr = r <= c ? r : c, cc = r <= c ? c : r;
+    T v = x[cc * (cc + 1) / 2 + rr];
+    if (r == c && has_scale) v *= scale;
+    a[idx] = v;
+}
+
+template <typename T>
+__global__ void shift_init_kernel(T* __restrict__ a, T* __restrict__ z, size_t k, T shift) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    size_t r = idx % k, c = idx / k;
+    if (r == c) { a[idx] += shift; z[idx] = T(1); }
+    else z[idx] = T(0);
+}
+
+// one tournament step: CTA `i` orthogonalises column pair (p, q) of G and applies the same rotation to V
+template <typename T>
+__global__ void __launch_bounds__(EG_THREADS) jacobi_step_kernel(T* __restrict__ g, T* __restrict__ v, int k, int kp, int step, double tol, unsigned int* rotations) {
+    __shared__ double red[3][EG_THREADS / 32];
+    __shared__ double cs[2];
+    const int i = blockIdx.x;
+    int p, q;
+    if (i == 0) { p = kp - 1; q = step; }
+    else { p = (step + i) % (kp - 1); q = (step - i + (kp - 1)) % (kp - 1); }
+    if (p >= k || q >= k) return;                  // dummy index of an odd-sized problem (uniform per CTA)
+    if (p > q) { int t = p; p = q; q = t; }
+    T* gp = g + (size_t)p * k;
+    T* gq = g + (size_t)q * k;
+    double al = 0.0, be = 0.0, ga = 0.0;
+    for (int r = threadIdx.x; r < k; r += EG_THREADS) {
+        double a = (double)gp[r], b = (double)gq[r];
+        al += a * a; be += b * b; ga += a * b;
+    }
+    al = tbd::warp_sum(al); be = tbd::warp_sum(be); ga = tbd::warp_sum(ga);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { red[0][w] = al; red[1][w] = be; red[2][w] = ga; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double A = 0, B = 0, G = 0;
+        for (int j = 0; j < EG_THREADS / 32; ++j) { A += red[0][j]; B += red[1][j]; G += red[2][j]; }
+        double c = 1.0, s = 0.0;
+        if (fabs(G) > tol * sqrt(A * B) && G != 0.0) {
+            double zeta = (B - A) / (2.0 * G);
+            double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = c * t;
+            atomicAdd(rotations, 1u);
+        }
+        cs[0] = c; cs[1] = s;
+    }
+    __syncthreads();
+    const double c = cs[0], s = cs[1];
+    if (s == 0.0) return;
+    T* vp = v + (size_t)p * k;
+    T* vq = v + (size_t)q * k;
+    for (int r = threadIdx.x; r < k; r += EG_THREADS) {
+        double a = (double)gp[r], b = (double)gq[r];
+        gp[r] = (T)(c * a - s * b);
+        gq[r] = (T)(s * a + c * b);
+        double x = (double)vp[r], y = (double)vq[r];
+        vp[r] = (T)(c * x - s * y);
+        vq[r] = (T)(s * x + c * y);
+    }
+}
+
+// w[i] = ||g_i|| - shift
+template <typename T>
+__global__ void __launch_bounds__(EG_THREADS) eigvals_kernel(const T* __restrict__ g, int k, double shift, T* __restrict__ w) {
+    __shared__ double red[32];
+    const T* gi = g + (size_t)blockIdx.x * k;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < k; r += EG_THREADS) { double a = (double)gi[r]; acc += a * a; }
+    double tot = tbd::block_sum(acc, red);
+    if (threadIdx.x == 0) w[blockIdx.x] = (T)(sqrt(tot) - shift);
+}
+
+// coef[i] = w[i] > 0 ? w[i] : 0   (ConePSD's closure, cone_psd.rs:69-76)
+template <typename T> __global__ void psd_coef_kernel(T* w, int k) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) { T e = w[i]; w[i] = e > T(0) ? e : T(0); }
+}
+
+// C(upper tiles) = Z * diag(coef) * Z^T ; Z, C column-major k x k.  64x64 tile per CTA, 4x4 per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) zdzt_kernel(const T* __restrict__ Z, const T* __restrict__ coef, int k, T* __restrict__ C) {
+    constexpr int TS = 64, KS = 16;
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (bi > bj) return;                           // only tiles touching the upper triangle
+    __shared__ T As[KS][TS + 4];
+    __shared__ T Bs[KS][TS + 4];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    const int i0 = bi * TS, j0 = bj * TS;
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+    for (int l0 = 0; l0 < k; l0 += KS) {
+        // 256 threads load 16 x 64 elements of each operand: thread -> (l = tid/16, 4 consecutive rows)
+        {
+            const int l = threadIdx.x / 16, r4 = (threadIdx.x % 16) * 4;
+            const int gl = l0 + l;
+            const T cf = gl < k ? coef[gl] : T(0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int gi = i0 + r4 + u, gj = j0 + r4 + u;
+                As[l][r4 + u] = (gl < k && gi < k) ? Z[(size_t)gl * k + gi] * cf : T(0);
+                Bs[l][r4 + u] = (gl < k && gj < k) ? Z[(size_t)gl * k + gj] : T(0);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < KS; ++l) {
+            T a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[l][ty * 4 + u]; b[u] = Bs[l][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) acc[u][w] += a[u] * b[w];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            int gi = i0 + ty * 4 + u, gj = j0 + tx * 4 + w;
+            if (gi < k && gj < k) C[(size_t)gj * k + gi] = acc[u][w];
+        }
+}
+
+template <typename T>
+__global__ void pack_kernel(const T* __restrict__ a, size_t k, int has_scale, T inv_scale, T* __restrict__ x) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    size_t r = idx % k, c = idx / k;
+    if (r > c) return;
+    T v = a[idx];
+    if (r == c && has_scale) v *= inv_scale;
+    x[c * (c + 1) / 2 + r] = v;
+}
+
+static size_t tri_dim(size_t sn) {
+    size_t n = (size_t)((std::sqrt((double)(8 * sn + 1)) - 1.0) / 2.0 + 0.5);
+    while (n * (n + 1) / 2 > sn) --n;
+    while ((n + 1) * (n + 2) / 2 <= sn) ++n;
+    return n;
+}
+
+// Steps 1-2: leaves eigenvalues in w (device), eigenvectors in z; returns nothing.  Syncs the stream.
+template <typename T> static void eig_decompose(const T* x, size_t k, bool has_scale, T scale, T* a, T* w, T* z) {
+    Context& c = ctx();
+    const size_t kk = k * k;
+    const unsigned gkk = (unsigned)((kk + 255) / 256);
+    unpack_kernel<T><<<gkk, 256, 0, c.stream>>>(x, k, has_scale ? 1 : 0, scale, a);
+    TB_LAUNCH_CHECK();
+    const double fro = std::sqrt(l1_sumsq_sync<T>(a, kk));
+    TB_REQUIRE(std::isfinite(fro), "map_eig: matrix has non-finite entries");
+    const double shift = fro * (1.0 + 1.0 / 64.0);
+    shift_init_kernel<T><<<gkk, 256, 0, c.stream>>>(a, z, k, (T)shift);
+    TB_LAUNCH_CHECK();
+    // the shift actually applied, after rounding to T
+    const double shift_applied = (double)(T)shift;
+    if (k > 1 && fro > 0.0) {
+        const int kp = (int)((k + 1) / 2 * 2);
+        const double tol = 8.0 * (sizeof(T) == 4 ? 1.1920929e-7 : 2.220446049250313e-16);
+        unsigned int* rot = c.tickets + 32;
+        const int max_sweeps = 40;
+        for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+            TB_CUDA(cudaMemsetAsync(rot, 0, sizeof(unsigned int), c.stream));
+            for (int step = 0; step < kp - 1; ++step) {
+                jacobi_step_kernel<T><<<kp / 2, EG_THREADS, 0, c.stream>>>(a, z, (int)k, kp, step, tol, rot);
+            }
+            TB_CUDA(cudaGetLastError());
+            count_launch(kp - 1);
+            TB_CUDA(cudaMemcpyAsync(c.mailbox_host, rot, sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+            TB_CUDA(cudaStreamSynchronize(c.stream));
+            if (*reinterpret_cast<unsigned int*>(c.mailbox_host) == 0) break;
+        }
+    }
+    eigvals_kernel<T><<<(unsigned)k, EG_THREADS, 0, c.stream>>>(a, (int)k, shift_applied, w);
+    TB_LAUNCH_CHECK();
+}
+
+// Steps 3-4 with coefficients already in w (device)
+template <typename T> static void eig_reconstruct(T* x, size_t k, bool has_scale, T scale, T* a, const T* w, const T* z) {
+    Context& c = ctx();
+    const size_t kk = k * k;
+    const unsigned tiles = (unsigned)((k + 63) / 64);
+    zdzt_kernel<T><<<dim3(tiles, tiles), 256, 0, c.stream>>>(z, w, (int)k, a);
+    TB_LAUNCH_CHECK();
+    pack_kernel<T><<<(unsigned)((kk + 255) / 256), 256, 0, c.stream>>>(a, k, has_scale ? 1 : 0, has_scale ? T(1) / scale : T(1), x);
+    TB_LAUNCH_CHECK();
+}
+
+template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len) {
+    (void)eps_zero;
+    const size_t k = tri_dim(sn);
+    TB_REQUIRE(k * (k + 1) / 2 == sn, "ConePSD: length is not a triangular number");       // cone_psd.rs:35
+    TB_REQUIRE(work_len >= 2 * k * k + k, "ConePSD: work shortage");                        // cone_psd.rs:58-61
+    if (k == 0) return;
+    T* a = work;
+    T* w = work + k * k;
+    T* z = w + k;
+    const T sq2 = (T)1.41421356237309504880;
+    eig_decompose<T>(x, k, true, sq2, a, w, z);
+    psd_coef_kernel<T><<<(unsigned)((k + 127) / 128), 128, 0, ctx().stream>>>(w, (int)k);
+    TB_LAUNCH_CHECK();
+    eig_reconstruct<T>(x, k, true, sq2, a, w, z);
+}
+template void psd_project<float>(float*, size_t, float, float*, size_t);
+template void psd_project<double>(double*, size_t, double, double*, size_t);
+
+template <typename T>
+static void api_map_eig_begin(tb_view mat, int has_scale, T scale_diag, T eps_zero, tb_view work, T* host_eigs) {
+    (void)eps_zero;
+    require_init();
+    const size_t k = tri_dim(mat.len);
+    TB_REQUIRE(k * (k + 1) / 2 == mat.len, "map_eig: length is not a triangular number");   // f64lapack.rs:177-178
+    TB_REQUIRE(work.len >= 2 * k * k + k, "map_eig: work shortage");                        // f64lapack.rs:180
+    const T* x = rptr<T>(mat);
+    T* wk = wptr<T>(work);
+    if (k == 0) return;
+    T* a = wk; T* w = wk + k * k; T* z = w + k;
+    eig_decompose<T>(x, k, has_scale != 0, scale_diag, a, w, z);
+    TB_CUDA(cudaMemcpyAsync(host_eigs, w, k * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+    TB_CUDA(cudaStreamSynchronize(ctx().stream));
+}
+
+template <typename T>
+static void api_map_eig_finish(tb_view mat, int has_scale, T scale_diag, tb_view work, const T* new_eigs, const uint8_t* keep) {
+    require_init();
+    const size_t k = tri_dim(mat.len);
+    TB_REQUIRE(k * (k + 1) / 2 == mat.len, "map_eig: length is not a triangular number");
+    TB_REQUIRE(work.len >= 2 * k * k + k, "map_eig: work shortage");
+    T* x = wptr<T>(mat, true);
+    T* wk = wptr<T>(work);
+    if (k == 0) return;
+    T* a = wk; T* w = wk + k * k; T* z = w + k;
+    std::vector<T> coef(k);
+    for (size_t i = 0; i < k; ++i) coef[i] = keep[i] ? new_eigs[i] : T(0);
+    TB_CUDA(cudaMemcpyAsync(w, coef.data(), k * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+    TB_CUDA(cudaStreamSynchronize(ctx().stream));     // coef is a stack-owned staging vector
+    eig_reconstruct<T>(x, k, has_scale != 0, scale_diag, a, w, z);
+}
+
+template <typename T> static void api_proj_psd(tb_view x, T eps_zero, tb_view work) {
+    require_init();
+    T* px = wptr<T>(x);
+    T* wk = wptr<T>(work);
+    psd_project<T>(px, x.len, eps_zero, wk, work.len);
+}
+
+}  // namespace tb
+
+using namespace tb;
+extern "C" {
+size_t tb_map_eig_worklen(size_t n) { return 2 * n * n + n; }    // f64lapack.rs:165-170 (len_a + len_w + len_z)
+int tb_map_eig_begin_f32(tb_view m, int hs, float sd, float ez, tb_view w, float* e) { return api([&] { api_map_eig_begin<float>(m, hs, sd, ez, w, e); }); }
+int tb_map_eig_begin_f64(tb_view m, int hs, double sd, double ez, tb_view w, double* e) { return api([&] { api_map_eig_begin<double>(m, hs, sd, ez, w, e); }); }
+int tb_map_eig_finish_f32(tb_view m, int hs, float sd, tb_view w, const float* ne, const uint8_t* k) { return api([&] { api_map_eig_finish<float>(m, hs, sd, w, ne, k); }); }
+int tb_map_eig_finish_f64(tb_view m, int hs, double sd, tb_view w, const double* ne, const uint8_t* k) { return api([&] { api_map_eig_finish<double>(m, hs, sd, w, ne, k); }); }
+int tb_proj_psd_f32(tb_view x, float ez, tb_view w) { return api([&] { api_proj_psd<float>(x, ez, w); }); }
+int tb_proj_psd_f64(tb_view x, double ez, tb_view w) { return api([&] { api_proj_psd<double>(x, ez, w); }); }
+}

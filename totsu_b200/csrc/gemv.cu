@@ -1,0 +1,729 @@
+// Dense matrix-vector products: LinAlgEx::transform_ge (totsu_core/src/linalg_ex.rs:23; CPU twin
+// totsu_f64lapack/src/f64lapack.rs:123-146 = cblas dgemv ColumnMajor lda=n_row; superseded GPU call
+// totsu_f32cuda/src/f32cuda.rs:144-171 = cublasSgemv_v2) and the fused device-resident dense Operator
+// (operator.rs:11-156) that the throughput configurations hand to the solver.
+//
+// The matvec is HBM-bound: one read of A per call, 2*m*n*sizeof(F) bytes per op/trans_op pair.
+//
+// Fast path (`stream_kernel`): persistent, warp-specialised kernel, one CTA per SM.
+//   * a producer warp streams column segments of A (TR rows x TC columns per stage, 32 KB) into a
+//     6-stage shared-memory ring with TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP),
+//     each lane issuing one 4 KB column segment; full/empty mbarriers per stage;
+//   * 8 consumer warps read the staged tile with 128-bit LDS:
+//       pass N (y = A x):   thread t owns rows 4t..4t+3 of the row chunk and keeps their partial sums in
+//                           registers across the whole column range of the work unit;
+//       pass T (y = A^T x): warp w owns column w of the tile, lanes stride down the rows against the x
+//                           chunk held in registers, one shuffle reduction per column;
+//     the two passes can run on the same staged tile, which is what tb_denseop_apply_pair uses to serve an
+//     op and a trans_op with a single read of A;
+//   * partial results go to a scratch buffer and a small finalize kernel adds them in a fixed order
+//     (no atomics: results are bit-reproducible), applying alpha/beta.
+// Generic path (`gemv_n_generic` / `gemv_t_generic`): plain coalesced LDG kernels for matrices whose
+// leading dimension / base address is not 16-byte aligned (e.g. the 63 x n blocks of ProbSOCP) or that are
+// too small to be worth a persistent launch.  Same two-stage deterministic reduction.
+#include "common.cuh"
+
+namespace tb {
+
+// -------------------------------------------------------------------------------------------------------
+// finalize: y[i] = alpha * sum_j part[j*ld + i] + beta*y[i]      (beta == 0: y is not read)
+// -------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void finalize_kernel(const T* __restrict__ part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+        T s = T(0);
+        for (int j = 0; j < nparts; ++j) s += part[(size_t)j * ld + i];
+        T r = alpha * s;
+        if (beta != T(0)) r += beta * y[i];
+        y[i] = r;
+    }
+}
+
+template <typename T> static void finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
+    if (len == 0) return;
+    int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
+    finalize_kernel<T><<<g, 256, 0, ctx().stream>>>(part, nparts, ld, len, alpha, beta, y);
+    TB_LAUNCH_CHECK();
+}
+
+// -------------------------------------------------------------------------------------------------------
+// generic kernels
+// -------------------------------------------------------------------------------------------------------
+// y-part[j][r] = sum_{c in split j} f(A[r,c]) * x[c];  thread per row.  ABS: f = |.| and x == 1 (absadd_rows).
+template <typename T, bool ABS>
+__global__ void gemv_n_generic(const T* __restrict__ A, size_t lda, size_t n_row, size_t n_col,
+                               const T* __restrict__ x, T* __restrict__ out, size_t ld_out, size_t cols_per_split,
+                               bool direct, T alpha, T beta) {
+    size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t c0 = (size_t)blockIdx.y * cols_per_split;
+    size_t c1 = c0 + cols_per_split < n_col ? c0 + cols_per_split : n_col;
+    if (r >= n_row) return;
+    const T* a = A + r;
+    T acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    size_t c = c0;
+    for (; c + 4 <= c1; c += 4) {
+        T a0 = a[(c + 0) * lda], a1 = a[(c + 1) * lda], a2 = a[(c + 2) * lda], a3 = a[(c + 3) * lda];
+        if (ABS) {
+            acc0 += fabs(a0); acc1 += fabs(a1); acc2 += fabs(a2); acc3 += fabs(a3);
+        } else {
+            acc0 += a0 * x[c + 0]; acc1 += a1 * x[c + 1]; acc2 += a2 * x[c + 2]; acc3 += a3 * x[c + 3];
+        }
+    }
+    for (; c < c1; ++c) {
+        T a0 = a[c * lda];
+        acc0 += ABS ? fabs(a0) : a0 * x[c];
+    }
+    T s = (acc0 + acc1) + (acc2 + acc3);
+    if (direct) {
+        T rr = alpha * s;
+        if (beta != T(0)) rr += beta * out[r];
+        out[r] = rr;
+    } else {
+        out[(size_t)blockIdx.y * ld_out + r] = s;
+    }
+}
+
+// out-part[j][c] = sum_{r in split j} f(A[r,c]) * x[r];  a CTA of 256 threads handles 8 columns.
+template <typename T, bool ABS>
+__global__ void gemv_t_generic(const T* __restrict__ A, size_t lda, size_t n_row, size_t n_col,
+                               const T* __restrict__ x, T* __restrict__ out, size_t ld_out, size_t rows_per_split,
+                               bool direct, T alpha, T beta) {
+    constexpr int CW = 8;
+    __shared__ T red[CW][8];
+    size_t cb = (size_t)blockIdx.x * CW;
+    size_t r0 = (size_t)blockIdx.y * rows_per_split;
+    size_t r1 = r0 + rows_per_split < n_row ? r0 + rows_per_split : n_row;
+    int ncol = (int)(n_col - cb < (size_t)CW ? n_col - cb : (size_t)CW);
+    T acc[CW];
+#pragma unroll
+    for (int k = 0; k < CW; ++k) acc[k] = 0;
+    const T* a = A + cb * lda;
+    if (ncol == CW) {
+        for (size_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+            T xv = ABS ? T(1) : x[r];
+            T v[CW];
+#pragma unroll
+            for (int k = 0; k < CW; ++k) v[k] = a[(size_t)k * lda + r];
+#pragma unroll
+            for (int k = 0; k < CW; ++k) acc[k] += (ABS ? fabs(v[k]) : v[k]) * xv;
+        }
+    } else {
+        for (size_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+            T xv = ABS ? T(1) : x[r];
+            for (int k = 0; k < ncol; ++k) {
+                T v = a[(size_t)k * lda + r];
+                acc[k] += (ABS ? fabs(v) : v) * xv;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < CW; ++k) {
+        T s = tbd::warp_sum(acc[k]);
+        if (lane == 0) red[k][w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < ncol) {
+        int k = threadIdx.x;
+        T s = T(0);
+        int nw = blockDim.x >> 5;
+        for (int i = 0; i < nw; ++i) s += red[k][i];
+        size_t c = cb + k;
+        if (direct) {
+            T rr = alpha * s;
+            if (beta != T(0)) rr += beta * out[c];
+            out[c] = rr;
+        } else {
+            out[(size_t)blockIdx.y * ld_out + c] = s;
+        }
+    }
+}
+
+// y = alpha * f(A) x + beta y  (N) on the generic path
+template <typename T, bool ABS>
+static void run_generic_n(const T* A, size_t lda, size_t n_row, size_t n_col, const T* x, T alpha, T beta, T* y) {
+    Context& c = ctx();
+    if (n_row == 0) return;
+    size_t row_blocks = (n_row + 127) / 128;
+    size_t want = ((size_t)c.sm_count * 2 + row_blocks - 1) / row_blocks;
+    size_t max_splits = std::max<size_t>(1, n_col / 64);
+    size_t splits = std::max<size_t>(1, std::min(want, max_splits));
+    splits = std::min<size_t>(splits, 65535);
+    size_t cps = (n_col + splits - 1) / splits;
+    splits = n_col == 0 ? 1 : (n_col + cps - 1) / cps;
+    dim3 grid((unsigned)row_blocks, (unsigned)splits);
+    if (splits == 1) {
+        gemv_n_generic<T, ABS><<<grid, 128, 0, c.stream>>>(A, lda, n_row, n_col, x, y, 0, std::max<size_t>(cps, 1), true, alpha, beta);
+        TB_LAUNCH_CHECK();
+    } else {
+        T* part = reinterpret_cast<T*>(scratch(splits * n_row * sizeof(T)));
+        gemv_n_generic<T, ABS><<<grid, 128, 0, c.stream>>>(A, lda, n_row, n_col, x, part, n_row, cps, false, alpha, beta);
+        TB_LAUNCH_CHECK();
+        finalize<T>(part, (int)splits, n_row, n_row, alpha, beta, y);
+    }
+}
+
+template <typename T, bool ABS>
+static void run_generic_t(const T* A, size_t lda, size_t n_row, size_t n_col, const T* x, T alpha, T beta, T* y) {
+    Context& c = ctx();
+    if (n_col == 0) return;
+    size_t col_groups = (n_col + 7) / 8;
+    size_t want = ((size_t)c.sm_count * 2 + col_groups - 1) / col_groups;
+    size_t max_splits = std::max<size_t>(1, n_row / 1024);
+    size_t splits = std::max<size_t>(1, std::min(want, max_splits));
+    splits = std::min<size_t>(splits, 65535);
+    size_t rps = (n_row + splits - 1) / splits;
+    splits = n_row == 0 ? 1 : (n_row + rps - 1) / rps;
+    TB_REQUIRE(col_groups <= 2147483647u, "too many columns");
+    dim3 grid((unsigned)col_groups, (unsigned)splits);
+    if (splits == 1) {
+        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, y, 0, std::max<size_t>(rps, 1), true, alpha, beta);
+        TB_LAUNCH_CHECK();
+    } else {
+        T* part = reinterpret_cast<T*>(scratch(splits * n_col * sizeof(T)));
+        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, part, n_col, rps, false, alpha, beta);
+        TB_LAUNCH_CHECK();
+        finalize<T>(part, (int)splits, n_col, n_col, alpha, beta, y);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// TMA streaming kernel
+// -------------------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+}  // namespace ptx
+
+template <typename T> struct StreamCfg;
+template <> struct StreamCfg<float> {
+    static constexpr int VEC = 4;
+    static constexpr int STAGES = 6;
+};
+template <> struct StreamCfg<double> {
+    static constexpr int VEC = 2;
+    static constexpr int STAGES = 6;
+};
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;   // 256
+constexpr int kTC = 8;                            // columns per tile == consumer warps
+constexpr int kStreamThreads = kConsumers + 32;   // + producer warp
+constexpr int kMaxUnitCols = 2048;                // x slice of a work unit staged in shared memory
+
+template <typename T> struct alignas(16) Vec16;
+template <> struct alignas(16) Vec16<float> { float v[4]; };
+template <> struct alignas(16) Vec16<double> { double v[2]; };
+
+struct StreamParams {
+    const void* A;
+    size_t lda, n_row, n_col;
+    const void* x_n;     // length n_col  (pass N), may be null
+    const void* x_t;     // length n_row  (pass T), may be null
+    void* part_n;        // [n_splits][n_row]
+    void* part_t;        // [n_chunks][n_col]
+    int n_chunks;        // row chunks of TR rows
+    int n_splits;        // column splits per row chunk
+    long long n_tiles;   // ceil(n_col / kTC): split s covers column tiles [n_tiles*s/n_splits, n_tiles*(s+1)/n_splits)
+    int n_units;         // n_chunks * n_splits
+};
+
+template <typename T, bool DO_N, bool DO_T>
+__global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamParams p) {
+    using Cfg = StreamCfg<T>;
+    constexpr int VEC = Cfg::VEC;
+    constexpr int TR = kConsumers * VEC;              // rows per tile (1024 f32 / 512 f64): 4 KB per column segment
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGE_ELEMS = TR * kTC;             // 32 KB
+    constexpr int KROW = TR / (32 * VEC);             // 8 row groups per lane in pass T
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* stage_base = reinterpret_cast<T*>(smem_raw);
+    T* xs = stage_base + (size_t)STAGES * STAGE_ELEMS;                                   // [kMaxUnitCols]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(xs + kMaxUnitCols);
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const T* __restrict__ A = reinterpret_cast<const T*>(p.A);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        ptx::mbar_fence_init();
+    }
+    __syncthreads();
+
+    // contiguous range of work units for this CTA; unit u = chunk * n_splits + split
+    const int u_begin = (int)(((long long)p.n_units * blockIdx.x) / gridDim.x);
+    const int u_end = (int)(((long long)p.n_units * (blockIdx.x + 1)) / gridDim.x);
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer warp =====================
+        const uint64_t pol = ptx::policy_evict_first();
+        int s = 0;
+        uint32_t phase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int chunk = u / p.n_splits, split = u - chunk * p.n_splits;
+            const size_t row0 = (size_t)chunk * TR;
+            const uint32_t rows = (uint32_t)(p.n_row - row0 < (size_t)TR ? p.n_row - row0 : (size_t)TR);
+            const size_t c0 = (size_t)kTC * (size_t)((p.n_tiles * split) / p.n_splits);
+            const size_t c1e = (size_t)kTC * (size_t)((p.n_tiles * (split + 1)) / p.n_splits);
+            const size_t c1 = c1e < p.n_col ? c1e : p.n_col;
+            for (size_t c = c0; c < c1; c += kTC) {
+                const int ncols = (int)(c1 - c < (size_t)kTC ? c1 - c : (size_t)kTC);
+                ptx::mbar_wait(&empty_bar[s], phase ^ 1);
+                if (lane == 0) ptx::mbar_expect_tx(&full_bar[s], rows * (uint32_t)sizeof(T) * (uint32_t)ncols);
+                __syncwarp();
+                if (lane < ncols)
+                    ptx::bulk_g2s(stage_base + (size_t)s * STAGE_ELEMS + (size_t)lane * TR, A + (c + lane) * p.lda + row0,
+                                  rows * (uint32_t)sizeof(T), &full_bar[s], pol);
+                if (++s == STAGES) { s = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== consumer warps =====================
+        const T* __restrict__ x_n = reinterpret_cast<const T*>(p.x_n);
+        const T* __restrict__ x_t = reinterpret_cast<const T*>(p.x_t);
+        T* __restrict__ part_n = reinterpret_cast<T*>(p.part_n);
+        T* __restrict__ part_t = reinterpret_cast<T*>(p.part_t);
+        int s = 0;
+        uint32_t phase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            const int chunk = u / p.n_splits, split = u - chunk * p.n_splits;
+            const size_t row0 = (size_t)chunk * TR;
+            const int rows = (int)(p.n_row - row0 < (size_t)TR ? p.n_row - row0 : (size_t)TR);
+            const size_t c0 = (size_t)kTC * (size_t)((p.n_tiles * split) / p.n_splits);
+            const size_t c1e = (size_t)kTC * (size_t)((p.n_tiles * (split + 1)) / p.n_splits);
+            const size_t c1 = c1e < p.n_col ? c1e : p.n_col;
+            const int ucols = (int)(c1 - c0);
+
+            if (DO_N) {
+                // stage this unit's slice of x (previous unit's readers are done: barrier first)
+                ptx::named_bar_sync(1, kConsumers);
+                for (int i = tid; i < ucols; i += kConsumers) xs[i] = x_n[c0 + i];
+                ptx::named_bar_sync(1, kConsumers);
+            }
+            // pass T: x chunk for the rows this lane strides over, rows beyond the matrix read as 0
+            T xr[KROW * VEC];
+            if (DO_T) {
+#pragma unroll
+                for (int k = 0; k < KROW; ++k)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        int r = (lane + 32 * k) * VEC + i;
+                        xr[k * VEC + i] = r < rows ? x_t[row0 + r] : T(0);
+                    }
+            }
+            T acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = T(0);
+            const bool row_ok = tid * VEC < rows;       // rows is a multiple of VEC
+
+            int cl = 0;   // column offset inside the unit
+            for (size_t c = c0; c < c1; c += kTC, cl += kTC) {
+                const int ncols = (int)(c1 - c < (size_t)kTC ? c1 - c : (size_t)kTC);
+                ptx::mbar_wait(&full_bar[s], phase);
+                const T* tile = stage_base + (size_t)s * STAGE_ELEMS;
+                if (DO_N && row_ok) {
+                    if (ncols == kTC) {
+                        Vec16<T> v[kTC];
+#pragma unroll
+                        for (int j = 0; j < kTC; ++j) v[j] = *reinterpret_cast<const Vec16<T>*>(tile + (size_t)j * TR + tid * VEC);
+#pragma unroll
+                        for (int j = 0; j < kTC; ++j) {
+                            T xv = xs[cl + j];
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[i] += v[j].v[i] * xv;
+                        }
+                    } else {
+                        for (int j = 0; j < ncols; ++j) {
+                            Vec16<T> v = *reinterpret_cast<const Vec16<T>*>(tile + (size_t)j * TR + tid * VEC);
+                            T xv = xs[cl + j];
+#pragma unroll
+                            for (int i = 0; i < VEC; ++i) acc[i] += v.v[i] * xv;
+                        }
+                    }
+                }
+                if (DO_T) {
+                    if (warp < ncols) {
+                        const T* col = tile + (size_t)warp * TR;
+                        T sum0 = T(0), sum1 = T(0);
+#pragma unroll
+                        for (int k = 0; k < KROW; ++k) {
+                            if ((lane + 32 * k) * VEC < rows) {
+                                Vec16<T> v = *reinterpret_cast<const Vec16<T>*>(col + (size_t)(lane + 32 * k) * VEC);
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) {
+                                    if ((k & 1) == 0) sum0 += v.v[i] * xr[k * VEC + i];
+                                    else sum1 += v.v[i] * xr[k * VEC + i];
+                                }
+                            }
+                        }
+                        T sum = tbd::warp_sum(sum0 + sum1);
+                        if (lane == 0) part_t[(size_t)chunk * p.n_col + c + warp] = sum;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+                if (++s == STAGES) { s = 0; phase ^= 1; }
+            }
+            if (DO_N && row_ok) {
+                T* dst = part_n + (size_t)split * p.n_row + row0 + (size_t)tid * VEC;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) dst[i] = acc[i];
+            }
+        }
+    }
+}
+
+template <typename T> static size_t stream_smem_bytes() {
+    using Cfg = StreamCfg<T>;
+    size_t stage = (size_t)kConsumers * Cfg::VEC * kTC * sizeof(T);
+    return stage * Cfg::STAGES + (size_t)kMaxUnitCols * sizeof(T) + 2 * Cfg::STAGES * sizeof(uint64_t) + 128;
+}
+
+template <typename T> static bool stream_eligible(const T* A, size_t lda, size_t n_row, size_t n_col) {
+    constexpr size_t VEC = 16 / sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return false;
+    if (lda % VEC != 0 || n_row % VEC != 0) return false;
+    if (n_row < 256 || n_col < 16) return false;
+    int mode = ctx().gemv_mode;
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    return n_row * n_col >= (size_t(1) << 20);
+}
+
+template <typename T, bool DO_N, bool DO_T> static void launch_stream(const StreamParams& p, int grid, size_t smem) {
+    static bool attr_set = false;     // one flag per kernel instantiation
+    if (!attr_set) {
+        TB_CUDA(cudaFuncSetAttribute(stream_kernel<T, DO_N, DO_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    Context& c = ctx();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c.prof_on) {
+        auto get_ev = [&]() {
+            cudaEvent_t e;
+            if (!c.prof_pool.empty()) { e = c.prof_pool.back(); c.prof_pool.pop_back(); }
+            else TB_CUDA(cudaEventCreate(&e));
+            return e;
+        };
+        e0 = get_ev(); e1 = get_ev();
+        TB_CUDA(cudaEventRecord(e0, c.stream));
+    }
+    stream_kernel<T, DO_N, DO_T><<<grid, kStreamThreads, smem, c.stream>>>(p);
+    TB_LAUNCH_CHECK();
+    if (c.prof_on) {
+        TB_CUDA(cudaEventRecord(e1, c.stream));
+        c.prof_pairs.push_back({e0, e1});
+        c.prof_bytes += (double)p.n_row * (double)p.n_col * sizeof(T);     // one read of A
+    }
+}
+
+static size_t gcd_sz(size_t a, size_t b) { while (b) { size_t t = a % b; a = b; b = t; } return a; }
+
+// Runs pass N and/or pass T over one read of A.  Outputs: y_n (len n_row), y_t (len n_col).
+template <typename T>
+static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
+                       const T* x_n, T alpha_n, T beta_n, T* y_n,
+                       const T* x_t, T alpha_t, T beta_t, T* y_t) {
+    Context& c = ctx();
+    constexpr int VEC = StreamCfg<T>::VEC;
+    constexpr size_t TR = (size_t)kConsumers * VEC;
+    const bool do_n = y_n != nullptr, do_t = y_t != nullptr;
+    const int n_cta = c.sm_count;
+    const size_t n_chunks = (n_row + TR - 1) / TR;
+    // column splits per row chunk: make n_chunks*n_splits a multiple of the CTA count (equal unit sizes ->
+    // balanced persistent CTAs), keep every unit's x slice within the shared-memory window
+    size_t base = (size_t)n_cta / gcd_sz(n_chunks, (size_t)n_cta);
+    size_t min_splits = (n_col + kMaxUnitCols - 1) / kMaxUnitCols;
+    size_t max_splits = std::max<size_t>(1, n_col / 32);
+    size_t n_splits = base;
+    while (n_splits < min_splits) n_splits += base;
+    // prefer >= 4 units per CTA when the matrix is wide enough
+    while (n_splits + base <= max_splits && n_chunks * n_splits < (size_t)4 * n_cta) n_splits += base;
+    if (n_splits > max_splits) n_splits = std::max(min_splits, max_splits);
+    const size_t n_tiles = (n_col + kTC - 1) / kTC;
+    n_splits = std::max<size_t>(1, std::min(n_splits, n_tiles));
+    TB_REQUIRE(((n_tiles + n_splits - 1) / n_splits) * kTC <= (size_t)kMaxUnitCols, "internal: unit too wide");
+
+    size_t bytes_n = do_n ? n_splits * n_row * sizeof(T) : 0;
+    size_t bytes_t = do_t ? n_chunks * n_col * sizeof(T) : 0;
+    bytes_n = (bytes_n + 255) & ~size_t(255);
+    char* sc = reinterpret_cast<char*>(scratch(bytes_n + bytes_t + 256));
+    StreamParams p;
+    p.A = A; p.lda = lda; p.n_row = n_row; p.n_col = n_col;
+    p.x_n = x_n; p.x_t = x_t;
+    p.part_n = sc; p.part_t = sc + bytes_n;
+    p.n_chunks = (int)n_chunks; p.n_splits = (int)n_splits; p.n_tiles = (long long)n_tiles;
+    p.n_units = (int)(n_chunks * n_splits);
+    int grid = std::min(n_cta, p.n_units);
+    size_t smem = stream_smem_bytes<T>();
+    if (do_n && do_t) launch_stream<T, true, true>(p, grid, smem);
+    else if (do_n) launch_stream<T, true, false>(p, grid, smem);
+    else launch_stream<T, false, true>(p, grid, smem);
+    if (do_n) finalize<T>(reinterpret_cast<const T*>(p.part_n), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n);
+    if (do_t) finalize<T>(reinterpret_cast<const T*>(p.part_t), (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
+}
+
+// y = alpha*op(A)*x + beta*y on device pointers (single GPU, no collectives)
+template <typename T>
+void gemv_dev(bool transpose, size_t n_row, size_t n_col, size_t lda, T alpha, const T* A, const T* x, T beta, T* y) {
+    if (stream_eligible<T>(A, lda, n_row, n_col)) {
+        if (!transpose) run_stream<T>(A, lda, n_row, n_col, x, alpha, beta, y, nullptr, T(0), T(0), nullptr);
+        else run_stream<T>(A, lda, n_row, n_col, nullptr, T(0), T(0), nullptr, x, alpha, beta, y);
+    } else {
+        if (!transpose) run_generic_n<T, false>(A, lda, n_row, n_col, x, alpha, beta, y);
+        else run_generic_t<T, false>(A, lda, n_row, n_col, x, alpha, beta, y);
+    }
+}
+
+template <typename T>
+void gemv_pair_dev(size_t n_row, size_t n_col, size_t lda, const T* A,
+                   T alpha_n, const T* x_n, T beta_n, T* y_n, T alpha_t, const T* x_t, T beta_t, T* y_t) {
+    if (stream_eligible<T>(A, lda, n_row, n_col)) {
+        run_stream<T>(A, lda, n_row, n_col, x_n, alpha_n, beta_n, y_n, x_t, alpha_t, beta_t, y_t);
+    } else {
+        run_generic_n<T, false>(A, lda, n_row, n_col, x_n, alpha_n, beta_n, y_n);
+        run_generic_t<T, false>(A, lda, n_row, n_col, x_t, alpha_t, beta_t, y_t);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------
+// LinAlgEx::transform_ge
+// -------------------------------------------------------------------------------------------------------
+template <typename T>
+static void api_transform_ge(int transpose, size_t n_row, size_t n_col, T alpha, tb_view mat, tb_view x, T beta, tb_view y) {
+    require_init();
+    TB_REQUIRE(mat.len == n_row * n_col, "transform_ge: mat.len != n_row*n_col");       // f64lapack.rs:125
+    if (transpose) {
+        TB_REQUIRE(x.len == n_row && y.len == n_col, "transform_ge(T): vector length mismatch");   // :128-129
+    } else {
+        TB_REQUIRE(x.len == n_col && y.len == n_row, "transform_ge(N): vector length mismatch");   // :133-134
+    }
+    const T* A = rptr<T>(mat);
+    const T* px = rptr<T>(x);
+    T* py = wptr<T>(y, beta == T(0));
+    if (y.len == 0) return;
+    if (n_row == 0 || n_col == 0) {          // dgemv quick return: y = beta*y
+        l1_scale<T>(beta, py, y.len);
+        return;
+    }
+    gemv_dev<T>(transpose != 0, n_row, n_col, n_row, alpha, A, px, beta, py);
+}
+
+// -------------------------------------------------------------------------------------------------------
+// Fused dense Operator (row-sharded across ranks when tb_dist_init'ed)
+// -------------------------------------------------------------------------------------------------------
+struct DenseOp {
+    int dtype;
+    tb_view mat;
+    size_t n_row, n_col;        // local shard
+    size_t row_offset, n_row_total;
+    void* tmp_n;                // n_col elements: local partial of A^T x before the all-reduce (sharded only)
+};
+
+static DenseOp& get_op(tb_handle h) {
+    Context& c = ctx();
+    if (h <= 0 || (size_t)h > c.denseops.size() || c.denseops[(size_t)h - 1] == nullptr) fail(TB_ERR_ARG, "invalid denseop handle");
+    return *c.denseops[(size_t)h - 1];
+}
+
+template <typename T> static void denseop_apply(tb_handle h, int transpose, T alpha, tb_view x, T beta, tb_view y) {
+    require_init();
+    DenseOp& op = get_op(h);
+    Context& c = ctx();
+    TB_REQUIRE(op.dtype == DT<T>::id, "denseop dtype mismatch");
+    const size_t m = op.n_row_total, n = op.n_col;
+    if (transpose) TB_REQUIRE(x.len == m && y.len == n, "denseop trans_op: vector length mismatch");
+    else TB_REQUIRE(x.len == n && y.len == m, "denseop op: vector length mismatch");
+    const T* A = rptr<T>(op.mat);
+    const T* px = rptr<T>(x);
+    T* py = wptr<T>(y, beta == T(0));
+    const bool sharded = c.world > 1 && op.n_row != op.n_row_total;
+    if (!sharded) {
+        gemv_dev<T>(transpose != 0, op.n_row, n, op.n_row, alpha, A, px, beta, py);
+        return;
+    }
+    if (!transpose) {
+        // local slice of y, then all-gather the slices (equal shard sizes, rank-major)
+        gemv_dev<T>(false, op.n_row, n, op.n_row, alpha, A, px, beta, py + op.row_offset);
+        dist_allgather_inplace(py, op.n_row, DT<T>::id);
+    } else {
+        // partial A_loc^T x_loc -> all-reduce -> y = alpha*sum + beta*y
+        T* tmp = reinterpret_cast<T*>(op.tmp_n);
+        gemv_dev<T>(true, op.n_row, n, op.n_row, T(1), A, px + op.row_offset, T(0), tmp);
+        dist_allreduce_sum(tmp, n, DT<T>::id);
+        l1_axpby<T>(alpha, tmp, beta, py, n);
+    }
+}
+
+template <typename T>
+static void denseop_apply_pair(tb_handle h, T alpha_n, tb_view x_n, T beta_n, tb_view y_n, T alpha_t, tb_view x_t, T beta_t, tb_view y_t) {
+    require_init();
+    DenseOp& op = get_op(h);
+    Context& c = ctx();
+    TB_REQUIRE(op.dtype == DT<T>::id, "denseop dtype mismatch");
+    const size_t m = op.n_row_total, n = op.n_col;
+    TB_REQUIRE(x_n.len == n && y_n.len == m && x_t.len == m && y_t.len == n, "denseop pair: vector length mismatch");
+    const bool sharded = c.world > 1 && op.n_row != op.n_row_total;
+    if (sharded) {
+        denseop_apply<T>(h, 0, alpha_n, x_n, beta_n, y_n);
+        denseop_apply<T>(h, 1, alpha_t, x_t, beta_t, y_t);
+        return;
+    }
+    const T* A = rptr<T>(op.mat);
+    const T* pxn = rptr<T>(x_n);
+    const T* pxt = rptr<T>(x_t);
+    T* pyn = wptr<T>(y_n, beta_n == T(0));
+    T* pyt = wptr<T>(y_t, beta_t == T(0));
+    gemv_pair_dev<T>(op.n_row, n, op.n_row, A, alpha_n, pxn, beta_n, pyn, alpha_t, pxt, beta_t, pyt);
+}
+
+template <typename T> static void denseop_absadd(tb_handle h, bool cols, tb_view v) {
+    require_init();
+    DenseOp& op = get_op(h);
+    Context& c = ctx();
+    TB_REQUIRE(op.dtype == DT<T>::id, "denseop dtype mismatch");
+    const T* A = rptr<T>(op.mat);
+    T* pv = wptr<T>(v);
+    const bool sharded = c.world > 1 && op.n_row != op.n_row_total;
+    if (cols) {
+        TB_REQUIRE(v.len == op.n_col, "absadd_cols: length mismatch");
+        if (!sharded) {
+            run_generic_t<T, true>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(1), pv);
+        } else {
+            T* tmp = reinterpret_cast<T*>(op.tmp_n);
+            run_generic_t<T, true>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(0), tmp);
+            dist_allreduce_sum(tmp, op.n_col, DT<T>::id);
+            l1_axpby<T>(T(1), tmp, T(1), pv, op.n_col);
+        }
+    } else {
+        TB_REQUIRE(v.len == op.n_row_total, "absadd_rows: length mismatch");
+        if (!sharded) {
+            run_generic_n<T, true>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(1), pv);
+        } else {
+            run_generic_n<T, true>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(1), pv + op.row_offset);
+            dist_allgather_inplace(pv, op.n_row, DT<T>::id);
+        }
+    }
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int tb_prof_enable(int on) {
+    return api([&] {
+        require_init();
+        ctx().prof_on = on != 0;
+    });
+}
+int tb_prof_read(uint64_t* launches, double* total_ms, double* total_bytes) {
+    return api([&] {
+        require_init();
+        Context& c = ctx();
+        TB_CUDA(cudaStreamSynchronize(c.stream));
+        for (auto& pr : c.prof_pairs) {
+            float ms = 0.f;
+            TB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            c.prof_ms += ms;
+            c.prof_launches += 1;
+            c.prof_pool.push_back(pr.first);
+            c.prof_pool.push_back(pr.second);
+        }
+        c.prof_pairs.clear();
+        *launches = c.prof_launches; *total_ms = c.prof_ms; *total_bytes = c.prof_bytes;
+        c.prof_launches = 0; c.prof_ms = 0.0; c.prof_bytes = 0.0;
+    });
+}
+
+int tb_transform_ge_f32(int tr, size_t nr, size_t nc, float a, tb_view m, tb_view x, float b, tb_view y) {
+    return api([&] { api_transform_ge<float>(tr, nr, nc, a, m, x, b, y); });
+}
+int tb_transform_ge_f64(int tr, size_t nr, size_t nc, double a, tb_view m, tb_view x, double b, tb_view y) {
+    return api([&] { api_transform_ge<double>(tr, nr, nc, a, m, x, b, y); });
+}
+
+int tb_denseop_create(int dtype, tb_view mat, size_t n_row, size_t n_col, size_t row_offset, size_t n_row_total, tb_handle* out) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(dtype == TB_F32 || dtype == TB_F64, "bad dtype");
+        TB_REQUIRE(mat.len == n_row * n_col, "denseop: mat.len != n_row*n_col");
+        if (n_row_total == 0) n_row_total = n_row;
+        TB_REQUIRE(row_offset + n_row <= n_row_total, "denseop: shard out of range");
+        Context& c = ctx();
+        if (c.world > 1 && n_row != n_row_total)
+            TB_REQUIRE(n_row * (size_t)c.world == n_row_total && row_offset == n_row * (size_t)c.rank,
+                       "denseop: row shards must be equal-sized and rank-ordered");
+        (void)dev_ptr(mat, dtype, false);
+        void* tmp = nullptr;
+        if (c.world > 1 && n_row != n_row_total) TB_CUDA(cudaMalloc(&tmp, std::max<size_t>(n_col, 1) * (dtype == TB_F32 ? 4 : 8)));
+        DenseOp* op = new DenseOp{dtype, mat, n_row, n_col, row_offset, n_row_total, tmp};
+        c.denseops.push_back(op);
+        *out = (tb_handle)c.denseops.size();
+    });
+}
+int tb_denseop_destroy(tb_handle h) {
+    return api([&] {
+        DenseOp& op = get_op(h);
+        if (op.tmp_n) { cudaStreamSynchronize(ctx().stream); cudaFree(op.tmp_n); }
+        delete &op;
+        ctx().denseops[(size_t)h - 1] = nullptr;
+    });
+}
+int tb_denseop_apply_f32(tb_handle op, int tr, float a, tb_view x, float b, tb_view y) { return api([&] { denseop_apply<float>(op, tr, a, x, b, y); }); }
+int tb_denseop_apply_f64(tb_handle op, int tr, double a, tb_view x, double b, tb_view y) { return api([&] { denseop_apply<double>(op, tr, a, x, b, y); }); }
+int tb_denseop_apply_pair_f32(tb_handle op, float an, tb_view xn, float bn, tb_view yn, float at, tb_view xt, float bt, tb_view yt) {
+    return api([&] { denseop_apply_pair<float>(op, an, xn, bn, yn, at, xt, bt, yt); });
+}
+int tb_denseop_apply_pair_f64(tb_handle op, double an, tb_view xn, double bn, tb_view yn, double at, tb_view xt, double bt, tb_view yt) {
+    return api([&] { denseop_apply_pair<double>(op, an, xn, bn, yn, at, xt, bt, yt); });
+}
+int tb_denseop_absadd_cols_f32(tb_handle op, tb_view tau) { return api([&] { denseop_absadd<float>(op, true, tau); }); }
+int tb_denseop_absadd_cols_f64(tb_handle op, tb_view tau) { return api([&] { denseop_absadd<double>(op, true, tau); }); }
+int tb_denseop_absadd_rows_f32(tb_handle op, tb_view s) { return api([&] { denseop_absadd<float>(op, false, s); }); }
+int tb_denseop_absadd_rows_f64(tb_handle op, tb_view s) { return api([&] { denseop_absadd<double>(op, false, s); }); }
+}
