@@ -49,12 +49,13 @@ def instance_vectors(nblk, bdim, n, seed):
     """x0, s0 in int K, y0 in int K* for the feasible-by-construction recipe."""
     rng = np.random.default_rng(seed + 12345)
     m = nblk * bdim
-    x0 = rng.standard_normal(n)
+    sc = 1.0 / math.sqrt(m)        # keeps ||b||, ||c|| = O(1): tau stays > 0 and criteria_conv runs every iteration
+    x0 = rng.standard_normal(n) * sc
 
     def interior():
         v = rng.standard_normal((nblk, bdim))
         v[:, 0] = np.linalg.norm(v[:, 1:], axis=1) + 1.0
-        return v.reshape(m)
+        return v.reshape(m) * sc
     return x0, interior(), interior()
 
 
@@ -209,8 +210,8 @@ def main():
         idbuf = (C.c_ubyte * capi.NCCL_ID_BYTES)(*t.cpu().tolist())
         capi.check(L.tb_dist_init(rank, world, idbuf))
         assert nblk % world == 0, "cone blocks must divide evenly across ranks"
-    m_loc = m // world
-    row_off = rank * m_loc
+    from totsu_b200 import shard
+    row_off, m_loc = shard.row_shards([(capi.CONE_SOC, bdim)] * nblk, world)[rank]
 
     # ---- instance: A generated in HBM (shard), b = A x0 + s0, c = -A^T y0 through the backend itself
     abuf = capi.Buf(dtype=dt, length=m_loc * n)
@@ -243,6 +244,12 @@ def main():
     # ---- device-resident timing: K iterations between two events on the library's stream
     s = new_session()
     assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+    if os.environ.get("BENCH_DEBUG"):
+        for _ in range(min(warmup, 5)):
+            s.step(1)
+            print("dbg iter %d tau %.4e res %.4e %.4e %.4e" % (s.last.i, s.last.val_tau, s.last.c0, s.last.c1, s.last.c2), file=sys.stderr)
+        print("dbg b[:4]", b[:4], "c[:4]", c[:4], "norms", s.norms(), file=sys.stderr)
+        warmup = max(0, warmup - 5)
     s.step(warmup)
     barrier()
     clocks = Clocks(local_rank) if rank == 0 else None
@@ -271,11 +278,15 @@ def main():
     t0 = time.perf_counter()
     st = s.begin(max_iter=steps, eps_acc=0.0, eps_inf=0.0, device_precond=True)
     assert st == "None"
+    t1 = time.perf_counter()
     st, _ = s.run()
+    t2 = time.perf_counter()
     s.end()
     xs, ys = s.solution()
     capi.check(L.tb_device_sync())
     t_e2e = time.perf_counter() - t0
+    if os.environ.get("BENCH_DEBUG"):
+        print("dbg e2e: begin %.4f s, run %.4f s, end+readback %.4f s" % (t1 - t0, t2 - t1, t0 + t_e2e - t2), file=sys.stderr)
     s.close()
     worklen = 4 * (n + 2 * m + 1) + 2 * (n + m + 1)
     h2d = worklen * esize / steps + 3 * esize          # work upload amortised + tau/kappa/unit scalars per iteration

@@ -46,9 +46,10 @@ struct SessionBase {
 };
 
 template <typename F> struct Session : SessionBase {
-    std::unique_ptr<Problem<F>> prob;       // owns operators, cone, work
-    // storage for raw/dense sessions
+    // storage for raw/dense sessions (declared first: outlives the operators wrapping it)
     std::vector<F> c_host, b_host;
+    Slice<F> c_dev, b_dev;                  // fused path: c and b wrapped once, served by DenseOp (n x 1, m x 1)
+    std::unique_ptr<Problem<F>> prob;       // owns operators, cone, work
     Solver<F> solver;
     std::vector<tbh_iter>* trace_sink = nullptr;
     int only_logged = 0;
@@ -222,11 +223,17 @@ SessionBase* make_dense(size_t m_local, size_t n, tb_view a_view, size_t row_off
     if (m_total == 0) m_total = m_local;
     s->c_host.assign(reinterpret_cast<const F*>(c), reinterpret_cast<const F*>(c) + n);
     s->b_host.assign(reinterpret_cast<const F*>(b), reinterpret_cast<const F*>(b) + m_total);
-    pr->op_c.reset(new VecOp<F>(std::unique_ptr<MatOp<F>>(new MatOp<F>(MatType::general(n, 1), s->c_host.data(), n))));
-    pr->op_b.reset(new VecOp<F>(std::unique_ptr<MatOp<F>>(new MatOp<F>(MatType::general(m_total, 1), s->b_host.data(), m_total))));
     if (fused_op) {
+        // c and b as device-resident n x 1 / m x 1 dense operators: their absadd_* run as kernels instead of one
+        // blocking strided abssum per element through the stock MatOp (matop.rs:105-116)
+        s->c_dev = Slice<F>::new_ref(s->c_host.data(), n);
+        s->b_dev = Slice<F>::new_ref(s->b_host.data(), m_total);
+        pr->op_c.reset(new DenseOp<F>(s->c_dev.view(), n, 1));
+        pr->op_b.reset(new DenseOp<F>(s->b_dev.view(), m_total, 1));
         pr->op_a.reset(new DenseOp<F>(a_view, m_local, n, row_offset, m_total));
     } else {
+        pr->op_c.reset(new VecOp<F>(std::unique_ptr<MatOp<F>>(new MatOp<F>(MatType::general(n, 1), s->c_host.data(), n))));
+        pr->op_b.reset(new VecOp<F>(std::unique_ptr<MatOp<F>>(new MatOp<F>(MatType::general(m_total, 1), s->b_host.data(), m_total))));
         if (m_local != m_total) throw BackendError("stock MatOp path cannot be row-sharded");
         pr->op_a.reset(new MatOp<F>(MatType::general(m_local, n), a_view));
     }

@@ -60,10 +60,11 @@ private:
 // ---------------------------------------------------------------------------------------------------------
 // A problem owns its operators, cone and solver work memory: `(op_c, op_a, op_b, cone, work)` of problem().
 template <typename F> struct Problem {
-    std::unique_ptr<Operator<F>> op_c, op_a, op_b;
-    std::unique_ptr<Cone<F>> cone;
+    // work memory first: it must outlive the cone / operators whose root slices flush into it when dropped
     std::vector<F> w_solver;
     std::vector<F> w_cone;
+    std::unique_ptr<Operator<F>> op_c, op_a, op_b;
+    std::unique_ptr<Cone<F>> cone;
     virtual ~Problem() = default;
 };
 
