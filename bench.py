@@ -302,10 +302,18 @@ def main():
     e2e_value = steps / t_e2e
     peak, peak_src = measured_peaks()
     roof = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.dtype == "f32" and world == 1:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+        tj = json.load(open(tpath))
+        vals = [v["dram_bytes_per_launch"] for k, v in tj.items() if k.startswith(args.workload + "|") and "stream_kernel" in k]
+        if vals:
+            traffic = sum(vals) / len(vals)
     if nl.value:
         ach = (kbytes.value / nl.value) / (kms.value / nl.value * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "stream_kernel (TMA bulk-copy matvec)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "launches_timed": int(nl.value), "avg_launch_ms": kms.value / nl.value,
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture)" if traffic else None, "peak_source": peak_src, "launches_timed": int(nl.value), "avg_launch_ms": kms.value / nl.value,
                 "algorithmic_bytes_per_launch": kbytes.value / nl.value}
     abytes_iter = 6.0 * m * n * esize
     line = {"metric": "solver iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
