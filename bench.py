@@ -210,6 +210,11 @@ def main():
         idbuf = (C.c_ubyte * capi.NCCL_ID_BYTES)(*t.cpu().tolist())
         capi.check(L.tb_dist_init(rank, world, idbuf))
         assert nblk % world == 0, "cone blocks must divide evenly across ranks"
+        p2p = C.c_int()
+        capi.check(L.tb_dist_p2p_enabled(C.byref(p2p)))
+        config["collectives"] = ("peer stores fused into the matvec epilogue (cudaIpc staging over NVLink)" if p2p.value
+                                 else "ncclAllGather / ncclAllReduce")
+        config["parallelism"] = "A row-sharded x%d on cone-block boundaries, vectors replicated" % world
     from totsu_b200 import shard
     row_off, m_loc = shard.row_shards([(capi.CONE_SOC, bdim)] * nblk, world)[rank]
 

@@ -68,6 +68,13 @@ int tb_buf_alloc(int dtype, size_t len, tb_handle* out);
 /* SliceLike::drop of a root slice: flush device-newer ranges to the host slice (if mutable) and free */
 int tb_buf_release(tb_handle buf);
 int tb_buf_len(tb_handle buf, size_t* out);
+/* For bindings whose slice type IS the host sub-slice (rust/totsu_b200: `B200Slice` is a transparent wrapper of
+ * `[F]`, so SliceLike::split_ref/split_mut (slicelike.rs:37-40) cost no allocation): find the wrapped root that
+ * contains host range [host, host + len) and return the view; a 0-length range yields the empty view {0,0,0}, which
+ * every entry point accepts.  tb_buf_retain adds `n` live wrappers to a root (one per non-empty child of a split);
+ * tb_buf_release removes one and only flushes + frees the root when none is left (slicelike.rs:18-19,42-46). */
+int tb_view_of_host(int dtype, const void* host, size_t len, tb_view* out);
+int tb_buf_retain(tb_handle buf, int n);
 /* SliceLike::get_ref / get_mut: make the host range current (D2H of device-newer sub-ranges);
  * get_mut additionally marks the range host-newer so the next device use re-uploads it */
 int tb_host_ref(tb_view v);
@@ -115,7 +122,10 @@ int tb_map_eig_begin_f32(tb_view mat, int has_scale, float scale_diag, float eps
 int tb_map_eig_begin_f64(tb_view mat, int has_scale, double scale_diag, double eps_zero, tb_view work, double* host_eigs);
 int tb_map_eig_finish_f32(tb_view mat, int has_scale, float scale_diag, tb_view work, const float* new_eigs, const uint8_t* keep);
 int tb_map_eig_finish_f64(tb_view mat, int has_scale, double scale_diag, tb_view work, const double* new_eigs, const uint8_t* keep);
-/* ConePSD::proj fast path (cone_psd.rs:56-79): the closure `e > 0 ? Some(e) : None` applied on the device */
+/* ConePSD::proj fast path (cone_psd.rs:56-79): the closure `e > 0 ? Some(e) : None` applied on the device.
+ * Default algorithm: GEMM-only matrix-sign iteration, proj = (X + X sign(X))/2, no host round trip;
+ * tb_set_psd_path(1) selects the Jacobi eigendecomposition that tb_map_eig_begin/finish use (tests compare both). */
+int tb_set_psd_path(int mode);
 int tb_proj_psd_f32(tb_view x, float eps_zero, tb_view work);
 int tb_proj_psd_f64(tb_view x, double eps_zero, tb_view work);
 
@@ -169,6 +179,9 @@ int tb_dist_unique_id(void* id_out /* TB_NCCL_ID_BYTES */);   /* rank 0, then br
 int tb_dist_init(int rank, int world, const void* id);
 int tb_dist_finalize(void);
 int tb_dist_info(int* rank, int* world);
+/* 1 when the sharded operator's all-gather / all-reduce run as peer stores fused into the matvec epilogue
+ * (cudaIpc-mapped staging over NVLink; TB_P2P=0 forces the NCCL baseline), 0 when they go through NCCL */
+int tb_dist_p2p_enabled(int* out);
 
 #ifdef __cplusplus
 }

@@ -117,7 +117,12 @@ def test_cone_psd_unit(dt):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("k", [1, 2, 3, 7, 16, 33, 64, 129])
-def test_proj_psd_vs_oracle(dt, k):
+@pytest.mark.parametrize("path", [0, 1])
+def test_proj_psd_vs_oracle(dt, k, path, request):
+    """path 0: GEMM-only matrix-sign iteration (the default), path 1: Jacobi eigendecomposition; both against the
+    oracle's dsyevr + dsyr restatement of f64lapack.rs:78-108."""
+    capi.check(capi.lib().tb_set_psd_path(path))
+    request.addfinalizer(lambda: capi.check(capi.lib().tb_set_psd_path(0)))
     rng = np.random.default_rng(k)
     g = rng.standard_normal((k, k))
     x = svec((g + g.T) / 2).astype(dt)
@@ -158,3 +163,63 @@ def test_map_eig_sqrt_closure(dt, k):
     capi.check(capi.fn("tb_map_eig_finish", dt)(mb.view(), 0, 1.0, wb.view(), new, keep))
     mb.release(); wb.release()
     assert np.abs(packed - want).max() <= (2e-3 if dt == np.float32 else 1e-10) * max(1.0, np.abs(want).max())
+
+
+def _spectrum_matrix(k, lam, seed):
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    x = (q * lam) @ q.T
+    return (x + x.T) / 2
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("name", ["logspaced", "lowrank", "psd_already", "neg_def", "near_boundary", "zero"])
+def test_proj_psd_hard_spectra(dt, name):
+    """Spectra that stress the sign iteration: eigenvalues spread over 12 decades on both sides of zero, rank
+    deficiency, inputs already inside / entirely outside the cone, iterates hugging the boundary, and X = 0."""
+    k = 96
+    rng = np.random.default_rng(3)
+    lam = {
+        "logspaced": np.concatenate([np.logspace(-12, 0, k // 2), -np.logspace(-12, 0, k // 2)]),
+        "lowrank": np.concatenate([np.ones(5), np.zeros(k - 5)]),
+        "psd_already": np.abs(rng.standard_normal(k)),
+        "neg_def": -np.abs(rng.standard_normal(k)) - 0.1,
+        "near_boundary": np.concatenate([rng.uniform(0.5, 1, k // 2), rng.standard_normal(k // 2) * 1e-6]),
+        "zero": np.zeros(k),
+    }[name]
+    x = svec(_spectrum_matrix(k, lam, 4)).astype(dt)
+    want = x.astype(np.float64).copy()
+    O.ConePSD(np.zeros(O.ConePSD.query_worklen(x.size)), 1e-12).proj(False, want)
+    scale = max(np.abs(x).max(), 1e-30)
+    xb, wb = capi.Buf(x), capi.Buf(np.zeros(2 * k * k + k, dtype=dt))
+    capi.check(capi.fn("tb_proj_psd", dt)(xb.view(), 1e-12, wb.view()))
+    xb.release(); wb.release()
+    assert np.isfinite(x).all()
+    tol = 2e-5 if dt == np.float32 else 1e-10
+    assert np.abs(x - want).max() <= tol * scale, (name, np.abs(x - want).max() / scale)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_proj_psd_c4_full_size(dt):
+    """Config C4's block: one ConePSD of 512 x 512 (sk = 131 328), against the oracle and by properties:
+    result is PSD, idempotent, and x - proj(x) is the projection of -x onto the cone reflected (Moreau)."""
+    k = 512
+    rng = np.random.default_rng(512)
+    g = rng.standard_normal((k, k))
+    x0 = svec((g + g.T) / 2).astype(dt)
+    want = x0.astype(np.float64).copy()
+    O.ConePSD(np.zeros(O.ConePSD.query_worklen(x0.size)), 1e-12).proj(False, want)
+    x = x0.copy()
+    xb, wb = capi.Buf(x), capi.Buf(np.zeros(2 * k * k + k, dtype=dt))
+    capi.check(capi.fn("tb_proj_psd", dt)(xb.view(), 1e-12, wb.view()))
+    xb.release(); wb.release()
+    tol = 5e-5 if dt == np.float32 else 1e-10
+    assert np.abs(x - want).max() <= tol * np.abs(want).max()
+    # Moreau decomposition: x0 = proj_K(x0) - proj_K(-x0), and <proj_K(x0), proj_K(-x0)> = 0
+    neg = (-x0).copy()
+    nb, wb = capi.Buf(neg), capi.Buf(np.zeros(2 * k * k + k, dtype=dt))
+    capi.check(capi.fn("tb_proj_psd", dt)(nb.view(), 1e-12, wb.view()))
+    nb.release(); wb.release()
+    assert np.abs((x.astype(np.float64) - neg.astype(np.float64)) - x0).max() <= 4 * tol * np.abs(x0).max()
+    ip = float(np.dot(x.astype(np.float64), neg.astype(np.float64)))
+    assert abs(ip) <= 50 * tol * float(np.dot(x.astype(np.float64), x.astype(np.float64)))

@@ -130,3 +130,38 @@ def test_recip_clamp(dt):
     buf.release()
     want = 1.0 / np.maximum(np.array([0.0, 1e-20, 0.5, 4.0, -3.0], dtype=dt), dt(1e-12))
     assert np.allclose(host, want, rtol=1e-6)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_view_of_host_and_wrapper_refcount(dt):
+    """The binding protocol of rust/totsu_b200 (B200Slice is the host sub-slice): sub-slices resolve to views by host
+    address, every non-empty wrapper holds a reference on its root, and the root is flushed to the caller's slice and
+    freed only when the last wrapper drops (slicelike.rs:18-19,37-46)."""
+    L = capi.lib()
+    work = np.arange(100, dtype=dt)
+    other = np.zeros(10, dtype=dt)
+    root = capi.Buf(work)                               # new_mut: refcount 1
+    ob = capi.Buf(other)
+    es = work.itemsize
+    v = capi.View()
+    capi.check(L.tb_view_of_host(capi.dtype_id(dt), C.c_void_p(work.ctypes.data + 20 * es), 30, C.byref(v)))
+    assert (v.buf, v.off, v.len) == (root.h, 20, 30)
+    capi.check(L.tb_view_of_host(capi.dtype_id(dt), C.c_void_p(other.ctypes.data), 10, C.byref(v)))
+    assert (v.buf, v.off, v.len) == (ob.h, 0, 10)
+    capi.check(L.tb_view_of_host(capi.dtype_id(dt), C.c_void_p(work.ctypes.data + 99 * es), 0, C.byref(v)))
+    assert (v.buf, v.off, v.len) == (0, 0, 0)           # empty slice -> the empty view, accepted everywhere
+    capi.check(capi.fn("tb_scale", dt)(2.0, v))
+    foreign = np.zeros(4, dtype=dt)
+    assert L.tb_view_of_host(capi.dtype_id(dt), C.c_void_p(foreign.ctypes.data), 4, C.byref(v)) != 0
+    # split_mut(20) -> two non-empty children, device work on one child, children drop, then the root
+    capi.check(L.tb_buf_retain(root.h, 2))
+    capi.check(L.tb_view_of_host(capi.dtype_id(dt), C.c_void_p(work.ctypes.data + 20 * es), 80, C.byref(v)))
+    capi.check(capi.fn("tb_scale", dt)(3.0, v))
+    capi.check(L.tb_buf_release(root.h))                # child a
+    capi.check(L.tb_buf_release(root.h))                # child b
+    assert work[20] == 20                               # nothing flushed yet: the root wrapper is still alive
+    size = C.c_size_t()
+    capi.check(L.tb_buf_len(root.h, C.byref(size)))     # handle still valid
+    root.release()                                      # last wrapper: flush + free
+    assert np.array_equal(work[:20], np.arange(20, dtype=dt)) and np.array_equal(work[20:], 3 * np.arange(20, 100, dtype=dt))
+    ob.release()

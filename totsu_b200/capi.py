@@ -52,17 +52,17 @@ def _signatures():
     sig = {
         "tb_init": (i, [i]), "tb_shutdown": (i, []), "tb_last_error": (C.c_char_p, []), "tb_device_sync": (i, []),
         "tb_get_stream": (i, [C.POINTER(vp)]), "tb_sm_count": (i, [C.POINTER(i)]),
-        "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]),
+        "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_psd_path": (i, [i]),
         "tb_prof_enable": (i, [i]), "tb_prof_read": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "tb_buf_wrap": (i, [i, vp, sz, i, C.POINTER(H)]), "tb_buf_alloc": (i, [i, sz, C.POINTER(H)]),
-        "tb_buf_release": (i, [H]), "tb_buf_len": (i, [H, C.POINTER(sz)]),
+        "tb_buf_release": (i, [H]), "tb_buf_retain": (i, [H, i]), "tb_view_of_host": (i, [i, vp, sz, C.POINTER(View)]), "tb_buf_len": (i, [H, C.POINTER(sz)]),
         "tb_host_ref": (i, [View]), "tb_host_mut": (i, [View]),
         "tb_upload": (i, [View, vp]), "tb_download": (i, [View, vp]),
         "tb_map_eig_worklen": (sz, [sz]),
         "tb_denseop_create": (i, [i, View, sz, sz, sz, sz, C.POINTER(H)]), "tb_denseop_destroy": (i, [H]),
         "tb_cone_create": (i, [C.POINTER(ConeBlock), sz, C.POINTER(H)]), "tb_cone_destroy": (i, [H]),
         "tb_dist_unique_id": (i, [vp]), "tb_dist_init": (i, [i, i, vp]), "tb_dist_finalize": (i, []),
-        "tb_dist_info": (i, [C.POINTER(i), C.POINTER(i)]),
+        "tb_dist_info": (i, [C.POINTER(i), C.POINTER(i)]), "tb_dist_p2p_enabled": (i, [C.POINTER(i)]),
     }
     for dt, F in _F.items():
         s = _SUF[dt]

@@ -87,6 +87,8 @@ struct Buffer {
     char* dev = nullptr;
     char* host = nullptr;      // caller-owned mirror, may be null (device-only)
     bool host_mut = false;
+    int refs = 1;              // live wrappers (root + sub-slices) when the binding counts them: tb_buf_retain/release
+    uint64_t gen = 0;          // creation order, newest wins an address lookup
     int small_slot = -1;       // >= 0: carved from the small-buffer slab, no cudaMalloc/cudaFree
     IntervalSet host_newer;    // host copy is newer than device
     IntervalSet dev_newer;     // device copy is newer than host
@@ -115,7 +117,12 @@ struct Context {
     static constexpr size_t kSmallBytes = 256;
     static constexpr int kSmallSlots = 1024;
     uint64_t launches = 0;
+    uint64_t buf_gen = 0;
+    tb_handle last_lookup = 0;
     int gemv_mode = 0;
+    int psd_mode = 0;                    // 0: matrix-sign iteration (GEMM-only), 1: Jacobi eigendecomposition
+    char* eig_scratch = nullptr;         // 3 k*k matrices for the sign iteration
+    size_t eig_scratch_bytes = 0;
     // event-pair profiling of the streaming matvec
     bool prof_on = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pairs;   // recorded, not yet read
@@ -172,10 +179,21 @@ template <typename T> void l1_scale(T alpha, T* x, size_t n);
 template <typename T> void l1_axpby(T alpha, const T* x, T beta, T* y, size_t n);   // y = alpha*x + beta*y (beta==0: y not read)
 template <typename T> void l1_copy(const T* x, T* y, size_t n);
 template <typename T> double l1_sumsq_sync(const T* x, size_t n);                   // returns sum of squares (double), syncs
+template <typename T> void l1_sumsq_async(const T* x, size_t n, double* out_dev);   // same, result stays on the device
 
-// ---- distributed internals ------------------------------------------------------------------------------
+// ---- level-2 internals ----------------------------------------------------------------------------------
+// y[i] = alpha * sum_j part[j*ld + i] + beta*y[i]   (fixed summation order; beta == 0: y is not read)
+template <typename T> void l2_finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y);
+
+// ---- distributed internals (dist.cu) --------------------------------------------------------------------
 void dist_allreduce_sum(void* buf, size_t count, int dtype);
 void dist_allgather_inplace(void* base, size_t count_per_rank, int dtype);   // rank r's slice lives at base + r*count
+// matvec epilogues fused with their collective (equal shard sizes, rank-major):
+//   gather: y_base[rank*len_local + i] = alpha*sum_j part[j*ld+i] + beta*(old value), then all ranks hold all slices
+//   reduce: y[i] = alpha * sum_ranks sum_j part[j*ld+i] + beta*y[i], summed in rank order on every rank
+template <typename T> void dist_finalize_gather(const T* part, int nparts, size_t ld, size_t len_local, T alpha, T beta, T* y_base);
+template <typename T> void dist_finalize_reduce(const T* part, int nparts, size_t ld, size_t n, T alpha, T beta, T* y);
+void dist_check_fault();      // throws if a peer-exchange wait timed out
 
 // ---- eig internals (cone.cu calls into eig.cu for PSD blocks) -------------------------------------------
 template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len);

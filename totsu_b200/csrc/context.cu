@@ -43,6 +43,7 @@ __global__ void poke_kernel(unsigned char* dst, SmallPayload p, unsigned int nby
 }
 
 char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite) {
+    if (v.buf == 0 && v.len == 0) return nullptr;       // the empty view (tb_view_of_host of a 0-length slice)
     Buffer& b = get_buf(v.buf);
     if (b.dtype != dtype) fail(TB_ERR_ARG, "view element type does not match the function suffix");
     if (v.off > b.len || v.len > b.len - v.off) fail(TB_ERR_ARG, "view out of range");
@@ -210,6 +211,7 @@ int tb_device_sync(void) {
     return api([&] {
         require_init();
         TB_CUDA(cudaStreamSynchronize(ctx().stream));
+        dist_check_fault();
     });
 }
 
@@ -258,6 +260,7 @@ int tb_buf_wrap(int dtype, void* host, size_t len, int host_is_mut, tb_handle* o
             throw;
         }
         b.alive = true;
+        b.gen = ++ctx().buf_gen;
         if (len > 0) b.host_newer.add(0, len);   // uploaded on first device use (or right away for big read-only data)
         if (!b.host_mut && len * b.esize >= (size_t(1) << 20)) {
             tb_view v{h, 0, len};
@@ -284,6 +287,7 @@ int tb_buf_alloc(int dtype, size_t len, tb_handle* out) {
             throw;
         }
         b.alive = true;
+        b.gen = ++ctx().buf_gen;
         TB_CUDA(cudaMemsetAsync(b.dev, 0, std::max<size_t>(len * b.esize, 0), ctx().stream));
         *out = h;
     });
@@ -294,6 +298,8 @@ int tb_buf_release(tb_handle h) {
         require_init();
         Buffer& b = get_buf(h);
         Context& c = ctx();
+        if (--b.refs > 0) return;                 // sub-slice wrappers of the binding are still alive
+        if (c.last_lookup == h) c.last_lookup = 0;
         if (b.host && b.host_mut) host_sync_range(b, 0, b.len);
         if (b.small_slot >= 0) {
             // slab slots are recycled without a device sync: every use is stream-ordered
@@ -307,6 +313,40 @@ int tb_buf_release(tb_handle h) {
     });
 }
 
+int tb_buf_retain(tb_handle h, int n) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(n >= 0, "retain count must be >= 0");
+        get_buf(h).refs += n;
+    });
+}
+
+int tb_view_of_host(int dtype, const void* host, size_t len, tb_view* out) {
+    return api([&] {
+        require_init();
+        Context& c = ctx();
+        if (len == 0) { *out = tb_view{0, 0, 0}; return; }
+        const size_t es = dtype == TB_F32 ? 4 : 8;
+        const char* lo = reinterpret_cast<const char*>(host);
+        const char* hi = lo + len * es;
+        auto covers = [&](const Buffer& b) {
+            return b.alive && b.host && b.dtype == dtype && b.host <= lo && hi <= b.host + b.len * b.esize;
+        };
+        tb_handle best = 0;
+        if (c.last_lookup > 0 && (size_t)c.last_lookup <= c.bufs.size() && covers(c.bufs[(size_t)c.last_lookup - 1])) {
+            best = c.last_lookup;
+        } else {
+            uint64_t best_gen = 0;
+            for (size_t i = 0; i < c.bufs.size(); ++i)
+                if (covers(c.bufs[i]) && c.bufs[i].gen > best_gen) { best = (tb_handle)(i + 1); best_gen = c.bufs[i].gen; }
+        }
+        if (best == 0) fail(TB_ERR_ARG, "tb_view_of_host: the host range is not inside any wrapped slice");
+        c.last_lookup = best;
+        const Buffer& b = c.bufs[(size_t)best - 1];
+        *out = tb_view{best, (size_t)(lo - b.host) / es, len};
+    });
+}
+
 int tb_buf_len(tb_handle h, size_t* out) {
     return api([&] {
         require_init();
@@ -317,6 +357,7 @@ int tb_buf_len(tb_handle h, size_t* out) {
 int tb_host_ref(tb_view v) {
     return api([&] {
         require_init();
+        if (v.buf == 0 && v.len == 0) return;
         Buffer& b = get_buf(v.buf);
         TB_REQUIRE(b.host != nullptr, "buffer has no host mirror");
         TB_REQUIRE(v.off <= b.len && v.len <= b.len - v.off, "view out of range");
@@ -327,6 +368,7 @@ int tb_host_ref(tb_view v) {
 int tb_host_mut(tb_view v) {
     return api([&] {
         require_init();
+        if (v.buf == 0 && v.len == 0) return;
         Buffer& b = get_buf(v.buf);
         TB_REQUIRE(b.host != nullptr && b.host_mut, "buffer has no mutable host mirror");
         TB_REQUIRE(v.off <= b.len && v.len <= b.len - v.off, "view out of range");

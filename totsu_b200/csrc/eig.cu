@@ -222,12 +222,179 @@ template <typename T> static void eig_reconstruct(T* x, size_t k, bool has_scale
     TB_LAUNCH_CHECK();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// ConePSD fast path: projection by the matrix sign function, GEMM-only, no host round trip.
+//
+//   proj_{S+}(X) = V max(L,0) V^T = (X + X sign(X)) / 2,       sign(X) = V sign(L) V^T.
+//
+// sign(X) comes from polynomial iterations on S0 = X/||X||_F (all iterates are polynomials in X: symmetric,
+// commuting, so only the upper tiles are computed and mirrored):
+//   phase 1  S <- S (a I + b S^2 + c S^4), (a,b,c) = (3.4445,-4.7750,2.0315): lifts an eigenvalue of relative
+//            size eps to O(1) in log(1/eps)/log(3.44) steps (3 GEMMs each);
+//   phase 2  S <- S (3 I - S^2)/2  (Newton-Schulz, 2 GEMMs): quadratic convergence of every |lambda| in (0, sqrt 3) to 1.
+// Eigenvalues below ~3.44^-n1 relative to ||X||_F stay unconverged; their contribution to the projection error is
+// bounded by their own magnitude, which is below the working precision for the step counts chosen here
+// (f32: 10 + 8 steps = 47 GEMMs, f64: 24 + 12 = 97).  For the reference this replaces dsyevr(V,V,U,(0,inf]) +
+// a dsyr loop (f64lapack.rs:78-108): same mathematical result, verified against the oracle in the tests.
+// The general closure path (tb_map_eig_begin/finish, e.g. MatBuild::set_sqrt) keeps the Jacobi eigensolver.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SG_TILE = 32;      // output tile
+constexpr int SG_KC = 64;        // K chunk per stage: 4 thread groups x 16
+constexpr int SG_THREADS = 256;
+
+// C = alpha * (A * B) + beta * D + gamma * I for symmetric k x k column-major A, B, D; C symmetric.
+// Since A = A^T:  C[i,j] = sum_l A[l*k + i] * B[l*k + j]  - both operands are read along contiguous columns.
+// 256 threads = 4 groups (split-K inside the chunk) x 64 threads (8 x 8, 4 x 4 micro-tile each).
+template <typename T>
+__global__ void __launch_bounds__(SG_THREADS) symm_gemm_kernel(const T* __restrict__ A, const T* __restrict__ B, const T* __restrict__ D,
+                                                                T* __restrict__ C, int k, T alpha, T beta, T gamma,
+                                                                const double* __restrict__ inv_norm_sq) {
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (bi > bj) return;
+    constexpr int RS = SG_TILE + 1;                            // padded row stride of the reduction tiles
+    __shared__ __align__(16) T smem[4 * SG_TILE * RS];         // As | Bs (2 * 64 * 32), later reused for the split-K reduction
+    T (*As)[SG_TILE] = reinterpret_cast<T (*)[SG_TILE]>(smem);
+    T (*Bs)[SG_TILE] = reinterpret_cast<T (*)[SG_TILE]>(smem + SG_KC * SG_TILE);
+    const int tid = threadIdx.x;
+    const int grp = tid >> 6, t64 = tid & 63;
+    const int tx = t64 & 7, ty = t64 >> 3;
+    const int i0 = bi * SG_TILE, j0 = bj * SG_TILE;
+    // loader mapping: thread -> (row l = tid / 4 in 0..63, 8 consecutive columns (tid % 4) * 8)
+    const int ll = tid >> 2, lc = (tid & 3) * 8;
+    T acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = T(0);
+    T ra[8], rb[8];
+    auto gload = [&](int l0) {
+        const int gl = l0 + ll;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int gi = i0 + lc + u, gj = j0 + lc + u;
+            ra[u] = (gl < k && gi < k) ? A[(size_t)gl * k + gi] : T(0);
+            rb[u] = (gl < k && gj < k) ? B[(size_t)gl * k + gj] : T(0);
+        }
+    };
+    gload(0);
+    for (int l0 = 0; l0 < k; l0 += SG_KC) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { As[ll][lc + u] = ra[u]; Bs[ll][lc + u] = rb[u]; }
+        __syncthreads();
+        if (l0 + SG_KC < k) gload(l0 + SG_KC);          // prefetch the next chunk while this one is consumed
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+            const int lr = grp * 16 + l;
+            T a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a[u] = As[lr][ty * 4 + u]; b[u] = Bs[lr][tx * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) acc[u][w] += a[u] * b[w];
+        }
+        __syncthreads();
+    }
+    // split-K reduction through shared memory: red[grp][i][j], padded rows
+    T* red = smem;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) red[(grp * SG_TILE + ty * 4 + u) * RS + tx * 4 + w] = acc[u][w];
+    __syncthreads();
+    // optional scaling by 1/||X||_F taken from device memory (first step only)
+    T al = alpha;
+    if (inv_norm_sq != nullptr) {
+        const double ss = *inv_norm_sq;
+        al = ss > 0.0 ? (T)((double)alpha / ss) : T(0);
+    }
+    // each thread finalises 4 entries: (i = tid % 32, j = tid / 32 + 8 q)
+    const int ii = tid & 31;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int jj = (tid >> 5) + 8 * q;
+        T v = red[(0 * SG_TILE + ii) * RS + jj] + red[(1 * SG_TILE + ii) * RS + jj] +
+              red[(2 * SG_TILE + ii) * RS + jj] + red[(3 * SG_TILE + ii) * RS + jj];
+        const int gi = i0 + ii, gj = j0 + jj;
+        if (gi < k && gj < k) {
+            v = al * v;
+            if (beta != T(0)) v += beta * D[(size_t)gj * k + gi];
+            if (gi == gj) v += gamma;
+            C[(size_t)gj * k + gi] = v;
+            if (bi != bj) C[(size_t)gi * k + gj] = v;    // mirror (strided store, 1/2 of the tiles only)
+        }
+    }
+}
+
+template <typename T>
+static void symm_gemm(const T* A, const T* B, const T* D, T* C, size_t k, T alpha, T beta, T gamma, const double* inv_norm_sq = nullptr) {
+    const unsigned nt = (unsigned)((k + SG_TILE - 1) / SG_TILE);
+    symm_gemm_kernel<T><<<dim3(nt, nt), SG_THREADS, 0, ctx().stream>>>(A, B, D, C, (int)k, alpha, beta, gamma, inv_norm_sq);
+    TB_LAUNCH_CHECK();
+}
+
+// s = x * rsqrt(sumsq)  (0 if the matrix is zero)
+template <typename T> __global__ void scale_inv_norm_kernel(const T* __restrict__ x, T* __restrict__ s, size_t n, const double* __restrict__ sumsq) {
+    const double ss = *sumsq;
+    const T inv = ss > 0.0 ? (T)(1.0 / sqrt(ss)) : T(0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s[i] = x[i] * inv;
+}
+
+static char* eig_scratch(size_t bytes) {
+    Context& c = ctx();
+    if (bytes > c.eig_scratch_bytes) {
+        TB_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.eig_scratch) TB_CUDA(cudaFree(c.eig_scratch));
+        TB_CUDA(cudaMalloc(&c.eig_scratch, bytes));
+        c.eig_scratch_bytes = bytes;
+    }
+    return c.eig_scratch;
+}
+
+template <typename T> static void psd_project_sign(T* x, size_t k, T* work) {
+    Context& c = ctx();
+    const size_t kk = k * k;
+    T* X = work;                 // unpacked, diagonal scaled by sqrt(2)
+    T* S0 = work + kk + k;       // the reference's z area
+    T* sc = reinterpret_cast<T*>(eig_scratch(3 * kk * sizeof(T)));
+    T* S1 = sc; T* T2 = sc + kk; T* P = sc + 2 * kk;
+    double* sumsq = c.mailbox_dev + 16;
+    const T sq2 = (T)1.41421356237309504880;
+    const unsigned gkk = (unsigned)((kk + 255) / 256);
+    unpack_kernel<T><<<gkk, 256, 0, c.stream>>>(x, k, 1, sq2, X);
+    TB_LAUNCH_CHECK();
+    l1_sumsq_async<T>(X, kk, sumsq);
+    scale_inv_norm_kernel<T><<<std::min<unsigned>(gkk, 4096u), 256, 0, c.stream>>>(X, S0, kk, sumsq);
+    TB_LAUNCH_CHECK();
+    const int n1 = sizeof(T) == 4 ? 10 : 24, n2 = sizeof(T) == 4 ? 8 : 12;
+    const T qa = (T)3.4445, qb = (T)-4.7750, qc = (T)2.0315;
+    T* S = S0; T* Sn = S1;
+    for (int it = 0; it < n1; ++it) {
+        symm_gemm<T>(S, S, nullptr, T2, k, T(1), T(0), T(0));            // T2 = S^2
+        symm_gemm<T>(T2, T2, T2, P, k, qc, qb, qa);                     // P = c S^4 + b S^2 + a I
+        symm_gemm<T>(S, P, nullptr, Sn, k, T(1), T(0), T(0));           // S' = S P
+        std::swap(S, Sn);
+    }
+    for (int it = 0; it < n2; ++it) {
+        symm_gemm<T>(S, S, nullptr, P, k, T(-0.5), T(0), T(1.5));       // P = 1.5 I - 0.5 S^2
+        symm_gemm<T>(S, P, nullptr, Sn, k, T(1), T(0), T(0));           // S' = S P
+        std::swap(S, Sn);
+    }
+    symm_gemm<T>(X, S, X, P, k, T(0.5), T(0.5), T(0));                  // proj = (X S + X) / 2
+    pack_kernel<T><<<gkk, 256, 0, c.stream>>>(P, k, 1, T(1) / sq2, x);
+    TB_LAUNCH_CHECK();
+}
+
 template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len) {
     (void)eps_zero;
     const size_t k = tri_dim(sn);
     TB_REQUIRE(k * (k + 1) / 2 == sn, "ConePSD: length is not a triangular number");       // cone_psd.rs:35
     TB_REQUIRE(work_len >= 2 * k * k + k, "ConePSD: work shortage");                        // cone_psd.rs:58-61
     if (k == 0) return;
+    if (ctx().psd_mode == 0 && k > 1) {
+        psd_project_sign<T>(x, k, work);
+        return;
+    }
     T* a = work;
     T* w = work + k * k;
     T* z = w + k;
@@ -284,6 +451,12 @@ template <typename T> static void api_proj_psd(tb_view x, T eps_zero, tb_view wo
 
 using namespace tb;
 extern "C" {
+int tb_set_psd_path(int mode) {
+    return api([&] {
+        TB_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (matrix-sign iteration) or 1 (Jacobi eigendecomposition)");
+        ctx().psd_mode = mode;
+    });
+}
 size_t tb_map_eig_worklen(size_t n) { return 2 * n * n + n; }    // f64lapack.rs:165-170 (len_a + len_w + len_z)
 int tb_map_eig_begin_f32(tb_view m, int hs, float sd, float ez, tb_view w, float* e) { return api([&] { api_map_eig_begin<float>(m, hs, sd, ez, w, e); }); }
 int tb_map_eig_begin_f64(tb_view m, int hs, double sd, double ez, tb_view w, double* e) { return api([&] { api_map_eig_begin<double>(m, hs, sd, ez, w, e); }); }

@@ -39,11 +39,16 @@ __global__ void finalize_kernel(const T* __restrict__ part, int nparts, size_t l
     }
 }
 
-template <typename T> static void finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
+template <typename T> void l2_finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
     if (len == 0) return;
     int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
     finalize_kernel<T><<<g, 256, 0, ctx().stream>>>(part, nparts, ld, len, alpha, beta, y);
     TB_LAUNCH_CHECK();
+}
+template void l2_finalize<float>(const float*, int, size_t, size_t, float, float, float*);
+template void l2_finalize<double>(const double*, int, size_t, size_t, double, double, double*);
+template <typename T> static void finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
+    l2_finalize<T>(part, nparts, ld, len, alpha, beta, y);
 }
 
 // -------------------------------------------------------------------------------------------------------
@@ -463,10 +468,12 @@ template <typename T, bool DO_N, bool DO_T> static void launch_stream(const Stre
 static size_t gcd_sz(size_t a, size_t b) { while (b) { size_t t = a % b; a = b; b = t; } return a; }
 
 // Runs pass N and/or pass T over one read of A.  Outputs: y_n (len n_row), y_t (len n_col).
+// `sharded`: A is this rank's row shard; y_n is then the BASE of the full-length vector (the local slice starts at
+// rank*n_row) and the epilogues carry the collective: all-gather of the slices / all-reduce of the partial sums.
 template <typename T>
 static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
                        const T* x_n, T alpha_n, T beta_n, T* y_n,
-                       const T* x_t, T alpha_t, T beta_t, T* y_t) {
+                       const T* x_t, T alpha_t, T beta_t, T* y_t, bool sharded = false) {
     Context& c = ctx();
     constexpr int VEC = StreamCfg<T>::VEC;
     constexpr size_t TR = (size_t)kConsumers * VEC;
@@ -502,6 +509,11 @@ static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
     if (do_n && do_t) launch_stream<T, true, true>(p, grid, smem);
     else if (do_n) launch_stream<T, true, false>(p, grid, smem);
     else launch_stream<T, false, true>(p, grid, smem);
+    if (sharded) {
+        if (do_n) dist_finalize_gather<T>(reinterpret_cast<const T*>(p.part_n), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n);
+        if (do_t) dist_finalize_reduce<T>(reinterpret_cast<const T*>(p.part_t), (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
+        return;
+    }
     if (do_n) finalize<T>(reinterpret_cast<const T*>(p.part_n), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n);
     if (do_t) finalize<T>(reinterpret_cast<const T*>(p.part_t), (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
 }
@@ -585,6 +597,13 @@ template <typename T> static void denseop_apply(tb_handle h, int transpose, T al
         gemv_dev<T>(transpose != 0, op.n_row, n, op.n_row, alpha, A, px, beta, py);
         return;
     }
+    const T* xl = px + op.row_offset;      // trans_op reads only the rows this rank owns
+    if (stream_eligible<T>(A, op.n_row, op.n_row, n)) {
+        // one streaming pass over the shard; the epilogue stores straight into the peers (dist.cu)
+        if (!transpose) run_stream<T>(A, op.n_row, op.n_row, n, px, alpha, beta, py, nullptr, T(0), T(0), nullptr, true);
+        else run_stream<T>(A, op.n_row, op.n_row, n, nullptr, T(0), T(0), nullptr, xl, alpha, beta, py, true);
+        return;
+    }
     if (!transpose) {
         // local slice of y, then all-gather the slices (equal shard sizes, rank-major)
         gemv_dev<T>(false, op.n_row, n, op.n_row, alpha, A, px, beta, py + op.row_offset);
@@ -592,7 +611,7 @@ template <typename T> static void denseop_apply(tb_handle h, int transpose, T al
     } else {
         // partial A_loc^T x_loc -> all-reduce -> y = alpha*sum + beta*y
         T* tmp = reinterpret_cast<T*>(op.tmp_n);
-        gemv_dev<T>(true, op.n_row, n, op.n_row, T(1), A, px + op.row_offset, T(0), tmp);
+        gemv_dev<T>(true, op.n_row, n, op.n_row, T(1), A, xl, T(0), tmp);
         dist_allreduce_sum(tmp, n, DT<T>::id);
         l1_axpby<T>(alpha, tmp, beta, py, n);
     }
@@ -608,6 +627,15 @@ static void denseop_apply_pair(tb_handle h, T alpha_n, tb_view x_n, T beta_n, tb
     TB_REQUIRE(x_n.len == n && y_n.len == m && x_t.len == m && y_t.len == n, "denseop pair: vector length mismatch");
     const bool sharded = c.world > 1 && op.n_row != op.n_row_total;
     if (sharded) {
+        const T* As = rptr<T>(op.mat);
+        if (stream_eligible<T>(As, op.n_row, op.n_row, n)) {
+            const T* sxn = rptr<T>(x_n);
+            const T* sxt = rptr<T>(x_t);
+            T* syn = wptr<T>(y_n, beta_n == T(0));
+            T* syt = wptr<T>(y_t, beta_t == T(0));
+            run_stream<T>(As, op.n_row, op.n_row, n, sxn, alpha_n, beta_n, syn, sxt + op.row_offset, alpha_t, beta_t, syt, true);
+            return;
+        }
         denseop_apply<T>(h, 0, alpha_n, x_n, beta_n, y_n);
         denseop_apply<T>(h, 1, alpha_t, x_t, beta_t, y_t);
         return;

@@ -92,6 +92,7 @@ template <typename T, int MODE> static double reduce_sync(const T* x, size_t cou
     TB_LAUNCH_CHECK();
     TB_CUDA(cudaMemcpyAsync(c.mailbox_host, c.mailbox_dev, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     TB_CUDA(cudaStreamSynchronize(c.stream));
+    dist_check_fault();
     return c.mailbox_host[0];
 }
 
@@ -117,6 +118,17 @@ template <typename T> void l1_axpby(T alpha, const T* x, T beta, T* y, size_t n)
     TB_LAUNCH_CHECK();
 }
 template <typename T> double l1_sumsq_sync(const T* x, size_t n) { return reduce_sync<T, 0>(x, n, 1); }
+// sum of squares left in device memory (*out_dev), no host round trip
+template <typename T> void l1_sumsq_async(const T* x, size_t n, double* out_dev) {
+    Context& c = ctx();
+    if (n == 0) { TB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), c.stream)); return; }
+    int g = grid_for(n, 8);
+    double* partials = reinterpret_cast<double*>(scratch((size_t)g * sizeof(double)));
+    reduce_kernel<T, 0><<<g, kThreads, 0, c.stream>>>(x, n, 1, partials, c.tickets, out_dev);
+    TB_LAUNCH_CHECK();
+}
+template void l1_sumsq_async<float>(const float*, size_t, double*);
+template void l1_sumsq_async<double>(const double*, size_t, double*);
 
 template void l1_scale<float>(float, float*, size_t);
 template void l1_scale<double>(double, double*, size_t);
