@@ -199,6 +199,7 @@ def main():
     torch.cuda.set_device(local_rank)
     capi.init(local_rank)
     L = capi.lib()
+    capi.check(L.tb_set_pair_fusion(1 if args.pair_fusion else 0))
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -270,7 +271,10 @@ def main():
     last = s.last
     # ---- the same region again with per-launch events around the streaming matvec (roofline numerator)
     capi.check(L.tb_prof_enable(1))
-    s.step(min(steps, 20))
+    prof_iters = min(steps, 20)
+    pf0 = capi.pairs_fused()
+    s.step(prof_iters)
+    pairs_per_iter = (capi.pairs_fused() - pf0) / prof_iters
     nl, kms, kbytes = C.c_uint64(), C.c_double(), C.c_double()
     capi.check(L.tb_prof_read(C.byref(nl), C.byref(kms), C.byref(kbytes)))
     capi.check(L.tb_prof_enable(0))
@@ -290,6 +294,7 @@ def main():
     xs, ys = s.solution()
     capi.check(L.tb_device_sync())
     t_e2e = time.perf_counter() - t0
+    t_e2e_local = t_e2e
     if os.environ.get("BENCH_DEBUG"):
         print("dbg e2e: begin %.4f s, run %.4f s, end+readback %.4f s" % (t1 - t0, t2 - t1, t0 + t_e2e - t2), file=sys.stderr)
     s.close()
@@ -316,19 +321,29 @@ def main():
         if vals:
             traffic = sum(vals) / len(vals)
     if nl.value:
-        ach = (kbytes.value / nl.value) / (kms.value / nl.value * 1e-3) / 1e9
+        # ALGORITHMIC bytes per launch: one read of this rank's A per op / trans_op served.  With the
+        # lazy pairing a launch serves an op AND a trans_op from ONE read of A, so the algorithmic figure is twice the
+        # bytes actually streamed and `frac` may exceed 1; `streamed_*` is the un-doubled DRAM-side figure.
+        avg_ms = kms.value / nl.value
+        alg_per_launch = 6.0 * prof_iters * m_loc * n * esize / nl.value
+        ach = alg_per_launch / (avg_ms * 1e-3) / 1e9
+        streamed = (kbytes.value / nl.value) / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "stream_kernel (TMA bulk-copy matvec)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture)" if traffic else None, "peak_source": peak_src, "launches_timed": int(nl.value), "avg_launch_ms": kms.value / nl.value,
-                "algorithmic_bytes_per_launch": kbytes.value / nl.value}
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture)" if traffic else None, "peak_source": peak_src, "launches_timed": int(nl.value), "avg_launch_ms": avg_ms,
+                "algorithmic_bytes_per_launch": alg_per_launch, "matvecs_per_launch": 6.0 * prof_iters / nl.value,
+                "streamed_bytes_per_launch": kbytes.value / nl.value, "streamed_gbs": streamed, "streamed_frac": streamed / peak,
+                "note": ("op/trans_op pairs share one read of A (lazy pairing behind tb_denseop_apply): achieved/frac use the un-fused "
+                         "algorithmic bytes and can exceed 1; streamed_frac is bytes actually read / peak") if pairs_per_iter else None}
     abytes_iter = 6.0 * m * n * esize
     line = {"metric": "solver iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "Solver::solve (begin + %d iterations + end) through the host layer, work/c/b in host memory" % steps},
+                    "what": "Solver::solve (begin + %d iterations + end) through the host layer, work/c/b in host memory" % steps,
+                    "breakdown_s": {"begin": t1 - t0, "iterate": t2 - t1, "end_and_readback": t0 + t_e2e_local - t2}},
             "gpu_launches": int(launches), "roofline": roof,
             "hbm_frac_whole_iteration": abytes_iter * value / (world * peak * 1e9),
-            "algorithmic_bytes_per_iteration": abytes_iter,
+            "algorithmic_bytes_per_iteration": abytes_iter, "pair_fusion": bool(args.pair_fusion), "pairs_fused_per_iteration": pairs_per_iter,
             "clocks": clk, "last_residuals": [last.c0, last.c1, last.c2], "status_e2e": st}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -58,6 +58,12 @@ int         tb_prof_enable(int on);
 int         tb_prof_read(uint64_t* launches, double* total_ms, double* total_bytes);
 /* tuning knob for tests: 0 = auto, 1 = force the generic (LDG) matvec, 2 = force the TMA matvec where legal */
 int         tb_set_gemv_path(int mode);
+/* Lazy op/trans_op pairing (default on): tb_denseop_apply parks the call until the opposite-direction apply on the
+ * same operator arrives (SelfDualEmbed::op / trans_op, solver.rs:128-131,150-153; criteria_conv :595-598) and then
+ * serves both with ONE read of A; calls in between are queued behind it and every host-visible call drains the
+ * queue first, so results are bit-identical to the unfused order.  0 restores launch-at-call behaviour. */
+int         tb_set_pair_fusion(int on);
+int         tb_pairs_fused(uint64_t* out);           /* pairs served by one pass since tb_init */
 
 /* ---- buffers: the SliceLike role (slicelike.rs:23-69; totsu_f32cuda/src/f32cuda_slice.rs:215-309) ------- */
 /* SliceLike::new_ref / new_mut: wrap caller-owned host memory with a device mirror.  The host slice stays

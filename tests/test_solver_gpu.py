@@ -200,3 +200,89 @@ def test_front_end_socp_matches_fused_dense(dt):
     s1.close(); s2.close(); abuf.release()
     tol = 1e-10 if dt == np.float64 else 2e-4
     assert H.rel_linf(x1, x2) <= tol and H.rel_linf(y1, y2) <= tol
+
+
+# ---- lazy op/trans_op pairing ------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_pair_fusion_bit_identical_and_counted(dt):
+    """tb_denseop_apply parks a call until its opposite-direction partner arrives and serves both with one read of A
+    (SelfDualEmbed::op / trans_op: solver.rs:128-131,150-153; criteria_conv: solver.rs:595-598).  The iterates must be
+    bit-identical to launch-at-call order, and every iteration must fuse exactly its 3 pairs."""
+    blocks, n = SYN["stream"]()
+    m = sum(l for _, l in blocks)
+    a, b, c = H.make_instance(m, n, blocks, seed=7, dtype=dt)
+    abuf, av = H.device_matrix(a)
+    L = capi.lib()
+    out = {}
+    try:
+        for fuse in (0, 1):
+            capi.check(L.tb_set_pair_fusion(fuse))
+            s = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=True, fused_cone=True)
+            assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+            p0 = capi.pairs_fused()
+            s.step(25)
+            out[fuse] = s.xy() + (capi.pairs_fused() - p0, (s.last.c0, s.last.c1, s.last.c2))
+            s.close()
+    finally:
+        capi.check(L.tb_set_pair_fusion(1))
+        abuf.release()
+    assert out[0][2] == 0 and out[1][2] == 3 * 25
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][3] == out[1][3]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_pair_fusion_hazards(dt):
+    """Deferred applies must respect data dependencies: a call that reads the parked apply's output, overwrites its
+    input, or is not a partner forces program order."""
+    rng = np.random.default_rng(11)
+    m, n = 2048, 512
+    a = np.asfortranarray(rng.standard_normal((m, n)).astype(dt))
+    abuf, av = H.device_matrix(a)
+    L = capi.lib()
+    import ctypes as C
+    h = C.c_int64()
+    capi.check(L.tb_denseop_create(capi.dtype_id(dt), av, m, n, 0, m, C.byref(h)))
+    ap = capi.fn("tb_denseop_apply", dt)
+    x = rng.standard_normal(n).astype(dt); u = rng.standard_normal(m).astype(dt)
+    a64 = a.astype(np.float64)
+    tol = 1e-11 if dt == np.float64 else 2e-4
+    try:
+        # (1) chain: y = A x ; v = A^T y   (partner READS the parked output -> no fusion, program order)
+        bx, by, bv = capi.Buf(x.copy()), capi.Buf(np.zeros(m, dt)), capi.Buf(np.zeros(n, dt))
+        p0 = capi.pairs_fused()
+        capi.check(ap(h.value, 0, 1.0, bx.view(), 0.0, by.view()))
+        capi.check(ap(h.value, 1, 1.0, by.view(), 0.0, bv.view()))
+        v = bv.download(); y = by.download()
+        assert capi.pairs_fused() == p0
+        assert H.rel_linf(y, a64 @ x) <= tol and H.rel_linf(v, a64.T @ (a64 @ x)) <= tol
+        # (2) the parked input is overwritten before the partner arrives: the parked apply must see the OLD x
+        capi.check(ap(h.value, 0, 1.0, bx.view(), 0.0, by.view()))
+        capi.check(capi.fn("tb_scale", dt)(0.0, bx.view()))
+        bu = capi.Buf(u.copy())
+        capi.check(ap(h.value, 1, 1.0, bu.view(), 0.0, bv.view()))
+        y = by.download(); v = bv.download()
+        assert H.rel_linf(y, a64 @ x) <= tol and H.rel_linf(v, a64.T @ u) <= tol
+        assert np.all(bx.download() == 0)
+        # (3) independent pair with an unrelated call in between and beta != 0 on both: fused, same numbers
+        bx.upload(x)
+        y0 = rng.standard_normal(m).astype(dt); v0 = rng.standard_normal(n).astype(dt)
+        by.upload(y0); bv.upload(v0)
+        bz = capi.Buf(np.ones(16, dt))
+        p0 = capi.pairs_fused()
+        capi.check(ap(h.value, 1, -0.5, bu.view(), 2.0, bv.view()))
+        capi.check(capi.fn("tb_scale", dt)(3.0, bz.view()))
+        capi.check(ap(h.value, 0, 1.5, bx.view(), -1.0, by.view()))
+        y = by.download(); v = bv.download()
+        assert capi.pairs_fused() == p0 + 1
+        assert H.rel_linf(y, 1.5 * (a64 @ x) - y0) <= tol and H.rel_linf(v, -0.5 * (a64.T @ u) + 2.0 * v0) <= tol
+        assert np.all(bz.download() == 3)
+        # (4) same direction twice: no fusion, both run
+        capi.check(ap(h.value, 0, 1.0, bx.view(), 0.0, by.view()))
+        capi.check(ap(h.value, 0, 2.0, bx.view(), 1.0, by.view()))
+        assert H.rel_linf(by.download(), 3.0 * (a64 @ x)) <= tol
+        for bf in (bx, by, bv, bu, bz):
+            bf.release()
+    finally:
+        capi.check(L.tb_denseop_destroy(h.value))
+        abuf.release()

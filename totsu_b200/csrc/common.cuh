@@ -7,6 +7,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <functional>
+#include <initializer_list>
 #include <stdexcept>
 #include <algorithm>
 #include "../../include/totsu_b200.h"
@@ -97,6 +99,28 @@ struct Buffer {
 struct DenseOp;
 struct ConeSet;
 
+// ---- lazy op/trans_op pairing ----------------------------------------------------------------------------
+// The solver calls A.trans_op and A.op back to back on independent vectors (SelfDualEmbed::op / trans_op,
+// solver.rs:128-131,150-153; criteria_conv, solver.rs:595-598), each a full read of A.  Behind the unmodified
+// trait surface the two calls arrive separately, so tb_denseop_apply does not launch at once: it parks the call
+// as the head of a small command queue.  Deferrable calls that follow (the c/b vector products in between) are
+// appended; when the opposite-direction apply on the same operator arrives and the data dependencies allow it to
+// be hoisted up to the head (or the head to be sunk down to it), both run as ONE streaming pass over A
+// (stream_kernel<T, true, true>).  Any call with a host-visible result, or one that does not fit the pattern,
+// drains the queue in program order first.  Results are bit-identical to the unfused sequence.
+struct Cmd {
+    tb_view reads[4];
+    tb_view writes[2];
+    int n_reads = 0, n_writes = 0;
+    std::function<void()> run;
+    // dense-apply metadata (is_dense): enough to re-issue it as half of a pair
+    bool is_dense = false;
+    tb_handle op = 0;
+    int trans = 0, dtype = 0;
+    double alpha = 0.0, beta = 0.0;
+    tb_view x{0, 0, 0}, y{0, 0, 0};
+};
+
 struct Context {
     bool inited = false;
     int device = 0;
@@ -131,6 +155,11 @@ struct Context {
     double prof_ms = 0.0, prof_bytes = 0.0;
     std::vector<DenseOp*> denseops;
     std::vector<ConeSet*> cones;
+    // deferred commands (see "lazy op/trans_op pairing" below); non-empty only while queue[0] is a dense apply
+    // waiting for its partner
+    std::vector<Cmd> queue;
+    bool pair_fusion = true;
+    uint64_t pairs_fused = 0;
     // distributed
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
@@ -161,7 +190,7 @@ inline void count_launch(int n = 1) { ctx().launches += (uint64_t)n; }
     } while (0)
 
 // API wrapper: translate internal exceptions to status codes.
-template <typename F> inline int api(F f) {
+template <typename F> inline int api_raw(F f) {
     try {
         f();
         return TB_OK;
@@ -173,6 +202,30 @@ template <typename F> inline int api(F f) {
         return TB_ERR_STATE;
     }
 }
+void queue_drain();     // run every deferred command in program order (context.cu)
+// Default entry-point wrapper: anything deferred runs first, then the call itself - used by every function that
+// returns a value to the host, manages buffers, or is not worth deferring.
+template <typename F> inline int api(F f) {
+    return api_raw([&] {
+        if (!ctx().queue.empty()) queue_drain();
+        f();
+    });
+}
+// Deferrable entry point: runs at once unless a dense apply is parked, in which case it queues behind it.
+// `f` must capture its arguments by value.
+template <typename F> inline int api_defer(std::initializer_list<tb_view> reads, std::initializer_list<tb_view> writes, F f) {
+    return api_raw([&] {
+        Context& c = ctx();
+        if (c.queue.empty()) { f(); return; }
+        Cmd cmd;
+        for (const tb_view& v : reads) cmd.reads[cmd.n_reads++] = v;
+        for (const tb_view& v : writes) cmd.writes[cmd.n_writes++] = v;
+        cmd.run = f;
+        c.queue.push_back(std::move(cmd));
+        if (c.queue.size() > 16) queue_drain();
+    });
+}
+bool cmds_conflict(const Cmd& a, const Cmd& b);
 
 // ---- level-1 internals reused across translation units -------------------------------------------------
 template <typename T> void l1_scale(T alpha, T* x, size_t n);

@@ -21,6 +21,29 @@ Buffer& get_buf(tb_handle h) {
     return c.bufs[(size_t)h - 1];
 }
 
+static inline bool views_overlap(const tb_view& a, const tb_view& b) {
+    return a.buf == b.buf && a.len > 0 && b.len > 0 && a.off < b.off + b.len && b.off < a.off + a.len;
+}
+
+// true if the two commands may not be reordered: one writes what the other reads or writes
+bool cmds_conflict(const Cmd& a, const Cmd& b) {
+    for (int i = 0; i < a.n_writes; ++i) {
+        for (int j = 0; j < b.n_reads; ++j) if (views_overlap(a.writes[i], b.reads[j])) return true;
+        for (int j = 0; j < b.n_writes; ++j) if (views_overlap(a.writes[i], b.writes[j])) return true;
+    }
+    for (int i = 0; i < b.n_writes; ++i)
+        for (int j = 0; j < a.n_reads; ++j) if (views_overlap(b.writes[i], a.reads[j])) return true;
+    return false;
+}
+
+void queue_drain() {
+    Context& c = ctx();
+    if (c.queue.empty()) return;
+    std::vector<Cmd> q;
+    q.swap(c.queue);                // a throwing command drops the rest: the error reaches the caller of this API call
+    for (Cmd& cmd : q) cmd.run();
+}
+
 void* scratch(size_t bytes) {
     Context& c = ctx();
     if (bytes > c.scratch_bytes) {
@@ -187,6 +210,7 @@ int tb_shutdown(void) {
     return api([&] {
         Context& c = ctx();
         if (!c.inited) return;
+        c.queue.clear();
         cudaStreamSynchronize(c.stream);
         for (Buffer& b : c.bufs)
             if (b.alive && b.small_slot < 0 && b.dev) cudaFree(b.dev);
@@ -231,6 +255,14 @@ int tb_sm_count(int* out) {
 
 int tb_launch_count(uint64_t* out) {
     return api([&] { *out = ctx().launches; });
+}
+
+int tb_set_pair_fusion(int on) {
+    return api([&] { ctx().pair_fusion = on != 0; });
+}
+
+int tb_pairs_fused(uint64_t* out) {
+    return api([&] { *out = ctx().pairs_fused; });
 }
 
 int tb_set_gemv_path(int mode) {

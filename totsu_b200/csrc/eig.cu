@@ -228,7 +228,7 @@ template <typename T> static void eig_reconstruct(T* x, size_t k, bool has_scale
 //   proj_{S+}(X) = V max(L,0) V^T = (X + X sign(X)) / 2,       sign(X) = V sign(L) V^T.
 //
 // sign(X) comes from polynomial iterations on S0 = X/||X||_F (all iterates are polynomials in X: symmetric,
-// commuting, so only the upper tiles are computed and mirrored):
+// commuting, so only the upper triangle is computed and mirrored - which also keeps the iterates exactly symmetric):
 //   phase 1  S <- S (a I + b S^2 + c S^4), (a,b,c) = (3.4445,-4.7750,2.0315): lifts an eigenvalue of relative
 //            size eps to O(1) in log(1/eps)/log(3.44) steps (3 GEMMs each);
 //   phase 2  S <- S (3 I - S^2)/2  (Newton-Schulz, 2 GEMMs): quadratic convergence of every |lambda| in (0, sqrt 3) to 1.
@@ -316,12 +316,15 @@ __global__ void __launch_bounds__(SG_THREADS) symm_gemm_kernel(const T* __restri
         T v = red[(0 * SG_TILE + ii) * RS + jj] + red[(1 * SG_TILE + ii) * RS + jj] +
               red[(2 * SG_TILE + ii) * RS + jj] + red[(3 * SG_TILE + ii) * RS + jj];
         const int gi = i0 + ii, gj = j0 + jj;
-        if (gi < k && gj < k) {
+        // Only entries on or above the diagonal are kept and then mirrored, so every iterate is EXACTLY symmetric:
+        // the kernel really computes A*B^T, and an antisymmetric rounding residue in S is amplified by the
+        // polynomial iterations (x3.4 per phase-1 step) until it destroys the result.
+        if (gi < k && gj < k && gi <= gj) {
             v = al * v;
             if (beta != T(0)) v += beta * D[(size_t)gj * k + gi];
             if (gi == gj) v += gamma;
             C[(size_t)gj * k + gi] = v;
-            if (bi != bj) C[(size_t)gi * k + gj] = v;    // mirror (strided store, 1/2 of the tiles only)
+            if (gi != gj) C[(size_t)gi * k + gj] = v;    // mirror
         }
     }
 }

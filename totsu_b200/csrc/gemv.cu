@@ -648,6 +648,67 @@ static void denseop_apply_pair(tb_handle h, T alpha_n, tb_view x_n, T beta_n, tb
     gemv_pair_dev<T>(op.n_row, n, op.n_row, A, alpha_n, pxn, beta_n, pyn, alpha_t, pxt, beta_t, pyt);
 }
 
+// tb_denseop_apply: park the call, or pair it with the parked one (see "lazy op/trans_op pairing", common.cuh)
+template <typename T> static void denseop_submit(tb_handle h, int transpose, T alpha, tb_view x, T beta, tb_view y) {
+    require_init();
+    Context& c = ctx();
+    DenseOp& op = get_op(h);
+    TB_REQUIRE(op.dtype == DT<T>::id, "denseop dtype mismatch");
+    const size_t m = op.n_row_total, n = op.n_col;
+    if (transpose) TB_REQUIRE(x.len == m && y.len == n, "denseop trans_op: vector length mismatch");
+    else TB_REQUIRE(x.len == n && y.len == m, "denseop op: vector length mismatch");
+    if (!c.pair_fusion) {
+        queue_drain();
+        denseop_apply<T>(h, transpose, alpha, x, beta, y);
+        return;
+    }
+    // only operators the streaming kernel serves are worth parking; the n x 1 / m x 1 operators that carry c and b
+    // on the fused route are ordinary deferrable commands (they sit BETWEEN the two halves of a pair)
+    const bool candidate = op.n_row >= 256 && op.n_col >= 16 && op.n_row * op.n_col >= (size_t(1) << 20);
+    Cmd cmd;
+    cmd.is_dense = true; cmd.op = h; cmd.trans = transpose ? 1 : 0; cmd.dtype = DT<T>::id;
+    cmd.alpha = (double)alpha; cmd.beta = (double)beta; cmd.x = x; cmd.y = y;
+    cmd.reads[cmd.n_reads++] = x;
+    cmd.reads[cmd.n_reads++] = op.mat;
+    if (beta != T(0)) cmd.reads[cmd.n_reads++] = y;
+    cmd.writes[cmd.n_writes++] = y;
+    cmd.run = [=] { denseop_apply<T>(h, transpose, alpha, x, beta, y); };
+    if (!candidate) {
+        if (c.queue.empty()) { cmd.run(); return; }
+        cmd.is_dense = false;
+        c.queue.push_back(std::move(cmd));
+        if (c.queue.size() > 16) queue_drain();
+        return;
+    }
+    if (!c.queue.empty()) {
+        const Cmd& head = c.queue[0];
+        bool fuse = head.is_dense && head.op == h && head.trans != cmd.trans && head.dtype == cmd.dtype && !cmds_conflict(head, cmd);
+        if (fuse) {
+            bool hoist_ok = true, sink_ok = true;
+            for (size_t i = 1; i < c.queue.size(); ++i) {
+                if (cmds_conflict(c.queue[i], cmd)) hoist_ok = false;
+                if (cmds_conflict(c.queue[i], head)) sink_ok = false;
+            }
+            if (hoist_ok || sink_ok) {
+                std::vector<Cmd> q;
+                q.swap(c.queue);
+                const Cmd& nn = q[0].trans ? cmd : q[0];      // the A*x half
+                const Cmd& tt = q[0].trans ? q[0] : cmd;      // the A^T*y half
+                auto pair = [&] {
+                    denseop_apply_pair<T>(h, (T)nn.alpha, nn.x, (T)nn.beta, nn.y, (T)tt.alpha, tt.x, (T)tt.beta, tt.y);
+                    c.pairs_fused += 1;
+                };
+                if (hoist_ok) pair();
+                for (size_t i = 1; i < q.size(); ++i) q[i].run();
+                if (!hoist_ok) pair();
+                return;
+            }
+        }
+        queue_drain();
+    }
+    c.queue.push_back(std::move(cmd));
+}
+
 template <typename T> static void denseop_absadd(tb_handle h, bool cols, tb_view v) {
     require_init();
     DenseOp& op = get_op(h);
@@ -709,10 +770,10 @@ int tb_prof_read(uint64_t* launches, double* total_ms, double* total_bytes) {
 }
 
 int tb_transform_ge_f32(int tr, size_t nr, size_t nc, float a, tb_view m, tb_view x, float b, tb_view y) {
-    return api([&] { api_transform_ge<float>(tr, nr, nc, a, m, x, b, y); });
+    return api_defer({m, x, y}, {y}, [=] { api_transform_ge<float>(tr, nr, nc, a, m, x, b, y); });
 }
 int tb_transform_ge_f64(int tr, size_t nr, size_t nc, double a, tb_view m, tb_view x, double b, tb_view y) {
-    return api([&] { api_transform_ge<double>(tr, nr, nc, a, m, x, b, y); });
+    return api_defer({m, x, y}, {y}, [=] { api_transform_ge<double>(tr, nr, nc, a, m, x, b, y); });
 }
 
 int tb_denseop_create(int dtype, tb_view mat, size_t n_row, size_t n_col, size_t row_offset, size_t n_row_total, tb_handle* out) {
@@ -742,8 +803,8 @@ int tb_denseop_destroy(tb_handle h) {
         ctx().denseops[(size_t)h - 1] = nullptr;
     });
 }
-int tb_denseop_apply_f32(tb_handle op, int tr, float a, tb_view x, float b, tb_view y) { return api([&] { denseop_apply<float>(op, tr, a, x, b, y); }); }
-int tb_denseop_apply_f64(tb_handle op, int tr, double a, tb_view x, double b, tb_view y) { return api([&] { denseop_apply<double>(op, tr, a, x, b, y); }); }
+int tb_denseop_apply_f32(tb_handle op, int tr, float a, tb_view x, float b, tb_view y) { return api_raw([&] { denseop_submit<float>(op, tr, a, x, b, y); }); }
+int tb_denseop_apply_f64(tb_handle op, int tr, double a, tb_view x, double b, tb_view y) { return api_raw([&] { denseop_submit<double>(op, tr, a, x, b, y); }); }
 int tb_denseop_apply_pair_f32(tb_handle op, float an, tb_view xn, float bn, tb_view yn, float at, tb_view xt, float bt, tb_view yt) {
     return api([&] { denseop_apply_pair<float>(op, an, xn, bn, yn, at, xt, bt, yt); });
 }

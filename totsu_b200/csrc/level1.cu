@@ -208,18 +208,18 @@ using namespace tb;
 extern "C" {
 int tb_norm_f32(tb_view x, float* out) { return api([&] { api_norm<float>(x, out); }); }
 int tb_norm_f64(tb_view x, double* out) { return api([&] { api_norm<double>(x, out); }); }
-int tb_copy_f32(tb_view x, tb_view y) { return api([&] { api_copy<float>(x, y); }); }
-int tb_copy_f64(tb_view x, tb_view y) { return api([&] { api_copy<double>(x, y); }); }
-int tb_scale_f32(float a, tb_view x) { return api([&] { api_scale<float>(a, x); }); }
-int tb_scale_f64(double a, tb_view x) { return api([&] { api_scale<double>(a, x); }); }
-int tb_add_f32(float a, tb_view x, tb_view y) { return api([&] { api_add<float>(a, x, y); }); }
-int tb_add_f64(double a, tb_view x, tb_view y) { return api([&] { api_add<double>(a, x, y); }); }
-int tb_adds_f32(float s, tb_view y) { return api([&] { api_adds<float>(s, y); }); }
-int tb_adds_f64(double s, tb_view y) { return api([&] { api_adds<double>(s, y); }); }
+int tb_copy_f32(tb_view x, tb_view y) { return api_defer({x}, {y}, [=] { api_copy<float>(x, y); }); }
+int tb_copy_f64(tb_view x, tb_view y) { return api_defer({x}, {y}, [=] { api_copy<double>(x, y); }); }
+int tb_scale_f32(float a, tb_view x) { return api_defer({x}, {x}, [=] { api_scale<float>(a, x); }); }
+int tb_scale_f64(double a, tb_view x) { return api_defer({x}, {x}, [=] { api_scale<double>(a, x); }); }
+int tb_add_f32(float a, tb_view x, tb_view y) { return api_defer({x, y}, {y}, [=] { api_add<float>(a, x, y); }); }
+int tb_add_f64(double a, tb_view x, tb_view y) { return api_defer({x, y}, {y}, [=] { api_add<double>(a, x, y); }); }
+int tb_adds_f32(float s, tb_view y) { return api_defer({y}, {y}, [=] { api_adds<float>(s, y); }); }
+int tb_adds_f64(double s, tb_view y) { return api_defer({y}, {y}, [=] { api_adds<double>(s, y); }); }
 int tb_abssum_f32(tb_view x, size_t incx, float* out) { return api([&] { api_abssum<float>(x, incx, out); }); }
 int tb_abssum_f64(tb_view x, size_t incx, double* out) { return api([&] { api_abssum<double>(x, incx, out); }); }
-int tb_transform_di_f32(float a, tb_view m, tb_view x, float b, tb_view y) { return api([&] { api_transform_di<float>(a, m, x, b, y); }); }
-int tb_transform_di_f64(double a, tb_view m, tb_view x, double b, tb_view y) { return api([&] { api_transform_di<double>(a, m, x, b, y); }); }
+int tb_transform_di_f32(float a, tb_view m, tb_view x, float b, tb_view y) { return api_defer({m, x, y}, {y}, [=] { api_transform_di<float>(a, m, x, b, y); }); }
+int tb_transform_di_f64(double a, tb_view m, tb_view x, double b, tb_view y) { return api_defer({m, x, y}, {y}, [=] { api_transform_di<double>(a, m, x, b, y); }); }
 int tb_recip_clamp_f32(float eps, tb_view x) { return api([&] { api_recip_clamp<float>(eps, x); }); }
 int tb_recip_clamp_f64(double eps, tb_view x) { return api([&] { api_recip_clamp<double>(eps, x); }); }
 }

@@ -121,6 +121,6 @@ template <typename T> static void api_transform_sp(size_t n, T alpha, tb_view ma
 
 using namespace tb;
 extern "C" {
-int tb_transform_sp_f32(size_t n, float a, tb_view m, tb_view x, float b, tb_view y) { return api([&] { api_transform_sp<float>(n, a, m, x, b, y); }); }
-int tb_transform_sp_f64(size_t n, double a, tb_view m, tb_view x, double b, tb_view y) { return api([&] { api_transform_sp<double>(n, a, m, x, b, y); }); }
+int tb_transform_sp_f32(size_t n, float a, tb_view m, tb_view x, float b, tb_view y) { return api_defer({m, x, y}, {y}, [=] { api_transform_sp<float>(n, a, m, x, b, y); }); }
+int tb_transform_sp_f64(size_t n, double a, tb_view m, tb_view x, double b, tb_view y) { return api_defer({m, x, y}, {y}, [=] { api_transform_sp<double>(n, a, m, x, b, y); }); }
 }
