@@ -134,7 +134,13 @@ struct Context {
     // scalar mailbox: pinned host memory for D2H of reduction results / get1
     double* mailbox_host = nullptr;
     double* mailbox_dev = nullptr;       // device-side staging for reduction results
-    unsigned int* tickets = nullptr;     // "last block done" counters
+    unsigned int* tickets = nullptr;     // "last block done" counters: [0,64) fixed roles, [64, 64+kTicketPool) per-group pool
+    static constexpr int kTicketPool = 4096;
+    // host box: 16 doubles of MAPPED pinned memory a kernel writes a host-visible scalar into (value at [0], then a
+    // sequence number at [1]); the host spins on the sequence number instead of cudaMemcpy + cudaStreamSynchronize
+    volatile double* hostbox = nullptr;
+    double* hostbox_dev = nullptr;       // device alias of hostbox
+    uint64_t box_seq = 0;
     // slab for tiny buffers (the solver wraps a 1-element slice every iteration: solver.rs:590-591)
     char* small_slab = nullptr;
     std::vector<int> small_free;
@@ -170,6 +176,10 @@ Context& ctx();
 void require_init();
 
 Buffer& get_buf(tb_handle h);
+// Host-visible scalar protocol: `uint64_t s = box_next();` -> launch a kernel that ends with box_post(hostbox_dev, v, s)
+// in exactly one thread -> `double v = box_wait(s);`
+uint64_t box_next();
+double box_wait(uint64_t seq);
 // Make [off, off+len) current on the device; if `write`, mark it device-newer.  Returns the device pointer
 // of element `off`.  `full_overwrite` skips the upload of host-newer data the kernel will overwrite anyway.
 char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite = false);
@@ -270,6 +280,13 @@ __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// publish a host-visible scalar: value first, then the sequence number the host spins on
+__device__ __forceinline__ void box_post(double* box, double v, unsigned long long seq) {
+    *reinterpret_cast<volatile double*>(box) = v;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(box + 1) = seq;
 }
 
 // Deterministic block-wide sum; result valid in thread 0 (and broadcast through smem to all).

@@ -44,6 +44,23 @@ void queue_drain() {
     for (Cmd& cmd : q) cmd.run();
 }
 
+uint64_t box_next() { return ++ctx().box_seq; }
+
+double box_wait(uint64_t seq) {
+    Context& c = ctx();
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(c.hostbox + 1);
+    for (unsigned long long spins = 0;; ++spins) {
+        if (*flag == seq) break;
+        if ((spins & 0xFFFF) == 0xFFFF) {
+            // every ~65k polls make sure the stream is still healthy: a faulted kernel never posts
+            cudaError_t e = cudaStreamQuery(c.stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) TB_CUDA(e);
+            if (e == cudaSuccess && *flag != seq) fail(TB_ERR_STATE, "host box: stream drained without a post");
+        }
+    }
+    return c.hostbox[0];
+}
+
 void* scratch(size_t bytes) {
     Context& c = ctx();
     if (bytes > c.scratch_bytes) {
@@ -130,6 +147,7 @@ static void host_sync_range(Buffer& b, size_t off, size_t len) {
 }
 
 template <typename T> __global__ void set1_kernel(T* p, T v) { *p = v; }
+template <typename T> __global__ void fetch1_kernel(const T* p, double* box, unsigned long long seq) { tbd::box_post(box, (double)*p, seq); }
 
 template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
     require_init();
@@ -142,9 +160,10 @@ template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
         *out = reinterpret_cast<const T*>(b.host)[i];
         return;
     }
-    TB_CUDA(cudaMemcpyAsync(c.mailbox_host, b.dev + i * b.esize, sizeof(T), cudaMemcpyDeviceToHost, c.stream));
-    TB_CUDA(cudaStreamSynchronize(c.stream));
-    *out = *reinterpret_cast<const T*>(c.mailbox_host);
+    const uint64_t seq = box_next();
+    fetch1_kernel<T><<<1, 1, 0, c.stream>>>(reinterpret_cast<const T*>(b.dev + i * b.esize), c.hostbox_dev, seq);
+    TB_LAUNCH_CHECK();
+    *out = (T)box_wait(seq);            // T -> double -> T is exact
     if (b.host && b.host_mut) {      // like SliceLike::get -> get_ref on the 1-element split: host copy becomes current
         reinterpret_cast<T*>(b.host)[i] = *out;
         b.dev_newer.sub(i, i + 1);
@@ -192,8 +211,18 @@ int tb_init(int device) {
         TB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         TB_CUDA(cudaHostAlloc(&c.mailbox_host, 64 * sizeof(double), cudaHostAllocDefault));
         TB_CUDA(cudaMalloc(&c.mailbox_dev, 64 * sizeof(double)));
-        TB_CUDA(cudaMalloc(&c.tickets, 64 * sizeof(unsigned int)));
-        TB_CUDA(cudaMemset(c.tickets, 0, 64 * sizeof(unsigned int)));
+        TB_CUDA(cudaMalloc(&c.tickets, (64 + Context::kTicketPool) * sizeof(unsigned int)));
+        TB_CUDA(cudaMemset(c.tickets, 0, (64 + Context::kTicketPool) * sizeof(unsigned int)));
+        {
+            void* hb = nullptr;
+            TB_CUDA(cudaHostAlloc(&hb, 16 * sizeof(double), cudaHostAllocMapped));
+            std::memset(hb, 0, 16 * sizeof(double));
+            c.hostbox = reinterpret_cast<volatile double*>(hb);
+            void* hd = nullptr;
+            TB_CUDA(cudaHostGetDevicePointer(&hd, hb, 0));
+            c.hostbox_dev = reinterpret_cast<double*>(hd);
+            c.box_seq = 0;
+        }
         TB_CUDA(cudaMalloc(&c.small_slab, Context::kSmallBytes * Context::kSmallSlots));
         TB_CUDA(cudaMemset(c.small_slab, 0, Context::kSmallBytes * Context::kSmallSlots));
         c.small_free.clear();
@@ -220,6 +249,8 @@ int tb_shutdown(void) {
         c.scratch = nullptr;
         c.scratch_bytes = 0;
         cudaFreeHost(c.mailbox_host);
+        cudaFreeHost((void*)c.hostbox);
+        c.hostbox = nullptr; c.hostbox_dev = nullptr;
         cudaFree(c.mailbox_dev);
         cudaFree(c.tickets);
         cudaFree(c.small_slab);

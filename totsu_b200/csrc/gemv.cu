@@ -51,6 +51,35 @@ template <typename T> static void finalize(const T* part, int nparts, size_t ld,
     l2_finalize<T>(part, nparts, ld, len, alpha, beta, y);
 }
 
+// both outputs of a paired pass in one launch: indices [0, len_a) finalize y_a, [len_a, len_a + len_b) finalize y_b
+template <typename T>
+__global__ void finalize2_kernel(const T* __restrict__ part_a, int nparts_a, size_t ld_a, size_t len_a, T alpha_a, T beta_a, T* y_a,
+                                 const T* __restrict__ part_b, int nparts_b, size_t ld_b, size_t len_b, T alpha_b, T beta_b, T* y_b) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len_a + len_b; i += (size_t)gridDim.x * blockDim.x) {
+        const bool first = i < len_a;
+        const T* part = first ? part_a : part_b;
+        const int nparts = first ? nparts_a : nparts_b;
+        const size_t ld = first ? ld_a : ld_b;
+        const size_t k = first ? i : i - len_a;
+        T s = T(0);
+        for (int j = 0; j < nparts; ++j) s += part[(size_t)j * ld + k];
+        const T alpha = first ? alpha_a : alpha_b, beta = first ? beta_a : beta_b;
+        T* y = first ? y_a : y_b;
+        T r = alpha * s;
+        if (beta != T(0)) r += beta * y[k];
+        y[k] = r;
+    }
+}
+template <typename T>
+static void finalize2(const T* part_a, int nparts_a, size_t ld_a, size_t len_a, T alpha_a, T beta_a, T* y_a,
+                      const T* part_b, int nparts_b, size_t ld_b, size_t len_b, T alpha_b, T beta_b, T* y_b) {
+    const size_t len = len_a + len_b;
+    if (len == 0) return;
+    int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
+    finalize2_kernel<T><<<g, 256, 0, ctx().stream>>>(part_a, nparts_a, ld_a, len_a, alpha_a, beta_a, y_a, part_b, nparts_b, ld_b, len_b, alpha_b, beta_b, y_b);
+    TB_LAUNCH_CHECK();
+}
+
 // -------------------------------------------------------------------------------------------------------
 // generic kernels
 // -------------------------------------------------------------------------------------------------------
@@ -92,9 +121,10 @@ __global__ void gemv_n_generic(const T* __restrict__ A, size_t lda, size_t n_row
 template <typename T, bool ABS>
 __global__ void gemv_t_generic(const T* __restrict__ A, size_t lda, size_t n_row, size_t n_col,
                                const T* __restrict__ x, T* __restrict__ out, size_t ld_out, size_t rows_per_split,
-                               bool direct, T alpha, T beta) {
+                               bool direct, T alpha, T beta, T* __restrict__ y_final, unsigned int* tickets) {
     constexpr int CW = 8;
     __shared__ T red[CW][8];
+    __shared__ bool last;
     size_t cb = (size_t)blockIdx.x * CW;
     size_t r0 = (size_t)blockIdx.y * rows_per_split;
     size_t r1 = r0 + rows_per_split < n_row ? r0 + rows_per_split : n_row;
@@ -142,6 +172,26 @@ __global__ void gemv_t_generic(const T* __restrict__ A, size_t lda, size_t n_row
             out[(size_t)blockIdx.y * ld_out + c] = s;
         }
     }
+    if (!direct && y_final != nullptr) {
+        // fused finalize: the last row-split block of this column group adds the partials in split order
+        // (deterministic) and applies alpha/beta
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned int t = atomicInc(&tickets[blockIdx.x], gridDim.y - 1);      // wraps back to 0
+            last = (t == gridDim.y - 1);
+        }
+        __syncthreads();
+        if (last && threadIdx.x < ncol) {
+            __threadfence();
+            const size_t c = cb + threadIdx.x;
+            T s = T(0);
+            for (unsigned int j = 0; j < gridDim.y; ++j) s += __ldcg(&out[(size_t)j * ld_out + c]);
+            T rr = alpha * s;
+            if (beta != T(0)) rr += beta * y_final[c];
+            y_final[c] = rr;
+        }
+    }
 }
 
 // y = alpha * f(A) x + beta y  (N) on the generic path
@@ -182,13 +232,15 @@ static void run_generic_t(const T* A, size_t lda, size_t n_row, size_t n_col, co
     TB_REQUIRE(col_groups <= 2147483647u, "too many columns");
     dim3 grid((unsigned)col_groups, (unsigned)splits);
     if (splits == 1) {
-        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, y, 0, std::max<size_t>(rps, 1), true, alpha, beta);
+        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, y, 0, std::max<size_t>(rps, 1), true, alpha, beta, nullptr, nullptr);
         TB_LAUNCH_CHECK();
     } else {
         T* part = reinterpret_cast<T*>(scratch(splits * n_col * sizeof(T)));
-        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, part, n_col, rps, false, alpha, beta);
+        const bool fused = col_groups <= (size_t)Context::kTicketPool;      // one ticket per column group
+        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, part, n_col, rps, false, alpha, beta,
+                                                           fused ? y : nullptr, c.tickets + 64);
         TB_LAUNCH_CHECK();
-        finalize<T>(part, (int)splits, n_col, n_col, alpha, beta, y);
+        if (!fused) finalize<T>(part, (int)splits, n_col, n_col, alpha, beta, y);
     }
 }
 
@@ -512,6 +564,11 @@ static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
     if (sharded) {
         if (do_n) dist_finalize_gather<T>(reinterpret_cast<const T*>(p.part_n), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n);
         if (do_t) dist_finalize_reduce<T>(reinterpret_cast<const T*>(p.part_t), (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
+        return;
+    }
+    if (do_n && do_t) {
+        finalize2<T>(reinterpret_cast<const T*>(p.part_n), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n,
+                     reinterpret_cast<const T*>(p.part_t), (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
         return;
     }
     if (do_n) finalize<T>(reinterpret_cast<const T*>(p.part_n), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n);

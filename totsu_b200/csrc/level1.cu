@@ -58,7 +58,8 @@ template <typename T> __global__ void recip_clamp_kernel(T eps, T* x, size_t n) 
 
 // MODE 0: sum of squares, MODE 1: sum of |x[i*inc]|
 template <typename T, int MODE>
-__global__ void reduce_kernel(const T* __restrict__ x, size_t count, size_t inc, double* partials, unsigned int* ticket, double* out) {
+__global__ void reduce_kernel(const T* __restrict__ x, size_t count, size_t inc, double* partials, unsigned int* ticket, double* out,
+                              double* box, unsigned long long seq) {
     __shared__ double red[32];
     __shared__ bool last;
     double acc = 0.0;
@@ -79,7 +80,10 @@ __global__ void reduce_kernel(const T* __restrict__ x, size_t count, size_t inc,
         double a = 0.0;
         for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += __ldcg(&partials[i]);
         double tot = tbd::block_sum(a, red);
-        if (threadIdx.x == 0) *out = tot;
+        if (threadIdx.x == 0) {
+            if (box != nullptr) tbd::box_post(box, tot, seq);     // host-visible: straight into mapped pinned memory
+            else *out = tot;
+        }
     }
 }
 
@@ -88,12 +92,12 @@ template <typename T, int MODE> static double reduce_sync(const T* x, size_t cou
     if (count == 0) return 0.0;
     int g = grid_for(count, 8);
     double* partials = reinterpret_cast<double*>(scratch((size_t)g * sizeof(double)));
-    reduce_kernel<T, MODE><<<g, kThreads, 0, c.stream>>>(x, count, inc, partials, c.tickets, c.mailbox_dev);
+    const uint64_t seq = box_next();
+    reduce_kernel<T, MODE><<<g, kThreads, 0, c.stream>>>(x, count, inc, partials, c.tickets, nullptr, c.hostbox_dev, seq);
     TB_LAUNCH_CHECK();
-    TB_CUDA(cudaMemcpyAsync(c.mailbox_host, c.mailbox_dev, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    TB_CUDA(cudaStreamSynchronize(c.stream));
+    const double r = box_wait(seq);
     dist_check_fault();
-    return c.mailbox_host[0];
+    return r;
 }
 
 template <typename T> void l1_scale(T alpha, T* x, size_t n) {
@@ -124,7 +128,7 @@ template <typename T> void l1_sumsq_async(const T* x, size_t n, double* out_dev)
     if (n == 0) { TB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), c.stream)); return; }
     int g = grid_for(n, 8);
     double* partials = reinterpret_cast<double*>(scratch((size_t)g * sizeof(double)));
-    reduce_kernel<T, 0><<<g, kThreads, 0, c.stream>>>(x, n, 1, partials, c.tickets, out_dev);
+    reduce_kernel<T, 0><<<g, kThreads, 0, c.stream>>>(x, n, 1, partials, c.tickets, out_dev, nullptr, 0ull);
     TB_LAUNCH_CHECK();
 }
 template void l1_sumsq_async<float>(const float*, size_t, double*);
