@@ -317,7 +317,8 @@ def main():
     if os.path.exists(tpath) and args.dtype == "f32" and world == 1:
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
         tj = json.load(open(tpath))
-        vals = [v["dram_bytes_per_launch"] for k, v in tj.items() if k.startswith(args.workload + "|") and "stream_kernel" in k]
+        want = "stream_kernel<float, 1, 1>" if pairs_per_iter else "stream_kernel<float, "
+        vals = [v["dram_bytes_per_launch"] for k, v in tj.items() if k.startswith(args.workload + "|") and want in k]
         if vals:
             traffic = sum(vals) / len(vals)
     if nl.value:
