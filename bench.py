@@ -28,9 +28,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n_blocks, block_dim, n)          m = n_blocks * block_dim
+    # name: (n_blocks, block_dim, n)          m = n_blocks * block_dim; block_dim == 1: ConeRPos(m) (an LP)
     "c3_socp_1024x64_A65536x16384": (1024, 64, 16384),
     "socp_small_128x64_A8192x4096": (128, 64, 4096),
+    "c5_lp_A262144x65536": (262144, 1, 65536),          # BASELINE config C5: 68.7 GB of A (f32), meant for 8 GPUs
+    "lp_A32768x65536": (32768, 1, 65536),               # one C5 shard on one GPU
 }
 DEFAULT_WORKLOAD = "c3_socp_1024x64_A65536x16384"
 SEED = 0
@@ -53,6 +55,8 @@ def instance_vectors(nblk, bdim, n, seed):
     x0 = rng.standard_normal(n) * sc
 
     def interior():
+        if bdim == 1:
+            return (np.abs(rng.standard_normal(m)) + 0.1) * sc
         v = rng.standard_normal((nblk, bdim))
         v[:, 0] = np.linalg.norm(v[:, 1:], axis=1) + 1.0
         return v.reshape(m) * sc
@@ -110,7 +114,7 @@ def cpu_reference_leg(nblk, bdim, n, steps, warmup, sample_blocks=None, threads=
     from totsu_b200 import synth
     cores = threads or os.cpu_count() or 1
     if sample_blocks is None:
-        sample_blocks = max(1, min(nblk, 64))
+        sample_blocks = max(1, min(nblk, 64 if bdim > 1 else 2048))
     ms = sample_blocks * bdim
     scale = np.float32(1.0 / math.sqrt(n))
     a32 = synth.uniform_matrix(ms, n, SEED, scale, dtype=np.float32)
@@ -118,6 +122,13 @@ def cpu_reference_leg(nblk, bdim, n, steps, warmup, sample_blocks=None, threads=
     a = a32.astype(np.float64)
     b = (a @ x0 + s0[:ms]).astype(np.float32).astype(np.float64)
     c = (-(a.T @ y0[:ms])).astype(np.float32).astype(np.float64)
+    if bdim == 1:
+        # ProbLP's shape (lp.rs:222-338): one MatOp G (ms x n) + ConeRPos(ms), no equalities
+        prob = O.ProbLP(O.MatBuild(O.MatType.General(n, 1), c), O.MatBuild(O.MatType.General(ms, n), np.asfortranarray(a).reshape(-1, order="F")),
+                        O.MatBuild(O.MatType.General(ms, 1), b), O.MatBuild(O.MatType.General(0, n)), O.MatBuild(O.MatType.General(0, 1)))
+        del a
+        return _time_oracle(O, prob, steps, warmup, cores, sample_blocks / nblk,
+                            "first %d of %d rows of the same A (f64, one dgemv per op like ProbLP, OpenBLAS via numpy instead of MKL)" % (ms, nblk))
     # ProbSOCP's shape (socp.rs:359-366): rows of block i = [-c_i^T; -G_i], h_i, d_i from b
     gs, hs, cs, ds = [], [], [], []
     for i in range(sample_blocks):
@@ -129,6 +140,12 @@ def cpu_reference_leg(nblk, bdim, n, steps, warmup, sample_blocks=None, threads=
     del a
     prob = O.ProbSOCP(O.MatBuild(O.MatType.General(n, 1), c), gs, hs, cs, ds,
                       O.MatBuild(O.MatType.General(0, n)), O.MatBuild(O.MatType.General(0, 1)))
+    return _time_oracle(O, prob, steps, warmup, cores, sample_blocks / nblk,
+                        "first %d of %d SOC blocks (%d x %d rows of the same A, f64, per-block dgemv like ProbSOCP, OpenBLAS via numpy instead of MKL)"
+                        % (sample_blocks, nblk, ms, n))
+
+
+def _time_oracle(O, prob, steps, warmup, cores, frac, what):
     s = O.Solver()
     s.par.max_iter = warmup + steps + 1
     s.par.eps_acc = 0.0
@@ -147,12 +164,9 @@ def cpu_reference_leg(nblk, bdim, n, steps, warmup, sample_blocks=None, threads=
     times.append(time.perf_counter())
     t = times[warmup:warmup + steps + 1]
     per_iter = (t[-1] - t[0]) / max(1, len(t) - 1)
-    it_per_s_sample = 1.0 / per_iter
-    value = it_per_s_sample * (sample_blocks / nblk)
+    value = (1.0 / per_iter) * frac
     return {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port",
-            "sample": "first %d of %d SOC blocks (%d x %d rows of the same A, f64, per-block dgemv like ProbSOCP, "
-                      "OpenBLAS via numpy instead of MKL); %d iterations timed, %.4f s/iter on the sample, scaled x%g linearly in rows"
-                      % (sample_blocks, nblk, ms, n, len(t) - 1, per_iter, sample_blocks / nblk)}
+            "sample": "%s; %d iterations timed, %.4f s/iter on the sample, scaled x%g linearly in rows" % (what, len(t) - 1, per_iter, frac)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -175,7 +189,7 @@ def main():
     nblk, bdim, n = WORKLOADS[args.workload]
     m = nblk * bdim
     steps, warmup = args.steps, max(args.warmup, 3)
-    config = {"workload": args.workload, "cone": "%d x ConeSOC(%d)" % (nblk, bdim), "A": "%d x %d dense column-major" % (m, n),
+    config = {"workload": args.workload, "cone": ("%d x ConeSOC(%d)" % (nblk, bdim)) if bdim > 1 else "ConeRPos(%d)" % m, "A": "%d x %d dense column-major" % (m, n),
               "l2": "A (%.2f GB) is larger than L2; no explicit flush" % (m * n * (4 if args.dtype == "f32" else 8) / 1e9)}
 
     if args.impl == "reference":
@@ -210,14 +224,14 @@ def main():
         dist.broadcast(t, 0)
         idbuf = (C.c_ubyte * capi.NCCL_ID_BYTES)(*t.cpu().tolist())
         capi.check(L.tb_dist_init(rank, world, idbuf))
-        assert nblk % world == 0, "cone blocks must divide evenly across ranks"
         p2p = C.c_int()
         capi.check(L.tb_dist_p2p_enabled(C.byref(p2p)))
         config["collectives"] = ("peer stores fused into the matvec epilogue (cudaIpc staging over NVLink)" if p2p.value
                                  else "ncclAllGather / ncclAllReduce")
         config["parallelism"] = "A row-sharded x%d on cone-block boundaries, vectors replicated" % world
     from totsu_b200 import shard
-    row_off, m_loc = shard.row_shards([(capi.CONE_SOC, bdim)] * nblk, world)[rank]
+    blocks = [(capi.CONE_SOC, bdim)] * nblk if bdim > 1 else [(capi.CONE_RPOS, m)]
+    row_off, m_loc = shard.row_shards(blocks, world)[rank]
 
     # ---- instance: A generated in HBM (shard), b = A x0 + s0, c = -A^T y0 through the backend itself
     abuf = capi.Buf(dtype=dt, length=m_loc * n)
@@ -233,7 +247,6 @@ def main():
     for bf in (bx, by, bb, bc):
         bf.release()
     capi.check(L.tb_denseop_destroy(hop.value))
-    blocks = [(capi.CONE_SOC, bdim)] * nblk
 
     stream = torch.cuda.ExternalStream(capi.stream_ptr(), device=torch.device("cuda", local_rank))
 

@@ -31,3 +31,18 @@ def test_sharded_operator_and_solver(p2p):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "dist_worker ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c5_full_size():
+    """BASELINE config C5 at full size (m = 262144, n = 65536; 68.7 GB of A row-sharded across all GPUs of the box)."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    port = 29900 + (os.getpid() % 90)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_c5_worker.py")]
+    r = subprocess.run(cmd, env=dict(os.environ), capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "dist_c5_worker ok" in r.stdout

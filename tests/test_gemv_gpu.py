@@ -229,3 +229,50 @@ def test_full_size_properties_c3():
     assert rel_linf(ax1[rows], sub @ x1.astype(np.float64)) <= 2e-5
     capi.check(L.tb_denseop_destroy(h.value))
     abuf.release()
+
+
+def test_full_size_properties_c5_single_gpu():
+    """BASELINE config C5's matrix (m = 262144, n = 65536, f32 = 68.7 GB) on ONE B200 (it fits the 180 GB of HBM;
+    the 8-GPU row-sharded form is tests/dist_c5_worker.py): adjoint identity, the fused pair equals the separate
+    passes bit for bit, run-to-run reproducibility, and sampled rows / columns against the numpy twin of the
+    generator - the oracle cannot hold this matrix (137 GB in f64)."""
+    import torch
+    free, total = torch.cuda.mem_get_info(0)
+    dt = np.float32
+    m, n = 262144, 65536
+    if free < m * n * 4 + (8 << 30):
+        pytest.skip("needs 77 GB of free HBM")
+    L = capi.lib()
+    rng = np.random.default_rng(5)
+    abuf = capi.Buf(dtype=dt, length=m * n)
+    scale = dt(1.0 / np.sqrt(n))
+    capi.check(L.tb_fill_uniform_f32(abuf.view(), m, n, 0, 5, scale))
+    h = C.c_int64()
+    capi.check(L.tb_denseop_create(capi.TB_F32, abuf.view(), m, n, 0, 0, C.byref(h)))
+    x = rng.standard_normal(n).astype(dt); u = rng.standard_normal(m).astype(dt)
+    xb, ub = capi.Buf(x.copy(), mutable=False), capi.Buf(u.copy(), mutable=False)
+    ax, atu, ax2, atu2 = (np.zeros(m, dt), np.zeros(n, dt), np.zeros(m, dt), np.zeros(n, dt))
+    b1, b2, b3, b4 = capi.Buf(ax), capi.Buf(atu), capi.Buf(ax2), capi.Buf(atu2)
+    capi.check(L.tb_set_pair_fusion(0))
+    try:
+        capi.check(L.tb_denseop_apply_f32(h.value, 0, 1.0, xb.view(), 0.0, b1.view()))
+        capi.check(L.tb_denseop_apply_f32(h.value, 1, 1.0, ub.view(), 0.0, b2.view()))
+    finally:
+        capi.check(L.tb_set_pair_fusion(1))
+    p0 = capi.pairs_fused()
+    capi.check(L.tb_denseop_apply_f32(h.value, 0, 1.0, xb.view(), 0.0, b3.view()))
+    capi.check(L.tb_denseop_apply_f32(h.value, 1, 1.0, ub.view(), 0.0, b4.view()))
+    for b in (b1, b2, b3, b4, xb, ub):
+        b.release()
+    assert capi.pairs_fused() == p0 + 1
+    assert np.array_equal(ax, ax2) and np.array_equal(atu, atu2)
+    lhs, rhs = np.dot(ax.astype(np.float64), u.astype(np.float64)), np.dot(x.astype(np.float64), atu.astype(np.float64))
+    assert abs(lhs - rhs) <= 1e-4 * (np.linalg.norm(ax) * np.linalg.norm(u))
+    rows = np.array([0, 1, 1023, 1024, 131071, 131072, 200001, 262143])
+    sub = synth.uniform_matrix(len(rows), n, 5, scale, dtype=dt, rows=rows).astype(np.float64)
+    assert rel_linf(ax[rows], sub @ x.astype(np.float64)) <= 5e-5
+    cols = np.array([0, 7, 8, 32767, 65535])
+    subc = synth.uniform_matrix(m, len(cols), 5, scale, dtype=dt, cols=cols).astype(np.float64)
+    assert rel_linf(atu[cols], subc.T @ u.astype(np.float64)) <= 5e-5
+    capi.check(L.tb_denseop_destroy(h.value))
+    abuf.release()
