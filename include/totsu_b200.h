@@ -132,6 +132,14 @@ int tb_map_eig_finish_f64(tb_view mat, int has_scale, double scale_diag, tb_view
  * Default algorithm: GEMM-only matrix-sign iteration, proj = (X + X sign(X))/2, no host round trip;
  * tb_set_psd_path(1) selects the Jacobi eigendecomposition that tb_map_eig_begin/finish use (tests compare both). */
 int tb_set_psd_path(int mode);
+/* The GEMM every step of the sign iteration is made of: C = alpha*A*B + beta*D + gamma*I with A, B, D symmetric k x k
+ * column-major (d.len == 0: no D term), C symmetric (upper triangle computed, mirrored).  engine 2 = tcgen05 3xTF32
+ * tensor-core kernel with split-K over a thread-block cluster (splitk 0 = choose, 1, 2 or 4; k % 4 == 0);
+ * engine 1 = FP32-pipe kernel.  f32 only (f64 stays on the FP64 pipe).  Replaces the dsyr rank-1 loop of
+ * f64lapack.rs:96-105 / the cublasSsyr loop of f32cuda.rs:316-324 inside ConePSD::proj; exported for the parity tests
+ * and the tensor-pipe measurement of config C4.  tb_set_psd_path: 0 = sign iteration (tcgen05 for f32), 1 = Jacobi,
+ * 2 = sign iteration on the FP32/FP64 pipes, 3 = tcgen05 without split-K. */
+int tb_symm_gemm_f32(size_t k, float alpha, tb_view a, tb_view b, float beta, tb_view d, float gamma, tb_view c, int engine, int splitk);
 int tb_proj_psd_f32(tb_view x, float eps_zero, tb_view work);
 int tb_proj_psd_f64(tb_view x, double eps_zero, tb_view work);
 

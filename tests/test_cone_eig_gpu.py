@@ -223,3 +223,79 @@ def test_proj_psd_c4_full_size(dt):
     assert np.abs((x.astype(np.float64) - neg.astype(np.float64)) - x0).max() <= 4 * tol * np.abs(x0).max()
     ip = float(np.dot(x.astype(np.float64), neg.astype(np.float64)))
     assert abs(ip) <= 50 * tol * float(np.dot(x.astype(np.float64), x.astype(np.float64)))
+
+
+# ---- tcgen05 engine of the sign iteration (csrc/psd_tc.cu) -------------------------------------------------
+def _sym32(rng, k):
+    g = rng.standard_normal((k, k))
+    return ((g + g.T) / 2).astype(np.float32)
+
+
+@pytest.mark.parametrize("k", [64, 128, 132, 200, 256, 384, 512, 640])
+@pytest.mark.parametrize("splitk", [0, 1, 2, 4])
+def test_symm_gemm_tcgen05_vs_numpy(k, splitk):
+    """C = alpha*A*B + beta*D + gamma*I on the tensor cores (3xTF32, split-K over a cluster) against numpy f64:
+    fp32-level accuracy (<= 2e-6 of max|C|; a single-pass TF32 product would sit near 1e-3), exactly symmetric
+    output, and bit-identical results run to run (fixed reduction order, no atomics)."""
+    L = capi.lib()
+    rng = np.random.default_rng(1000 * k + splitk)
+    a, b, d = _sym32(rng, k), _sym32(rng, k), _sym32(rng, k)
+    bufs = [capi.Buf(m.reshape(-1, order="F").copy(), mutable=False) for m in (a, b, d)]
+    alpha, beta, gamma = 0.75, -0.5, 1.25
+    outs = []
+    for _ in range(2):
+        c = np.zeros(k * k, dtype=np.float32)
+        cb = capi.Buf(c)
+        capi.check(L.tb_symm_gemm_f32(k, alpha, bufs[0].view(), bufs[1].view(), beta, bufs[2].view(), gamma, cb.view(), 2, splitk))
+        cb.release()
+        outs.append(c.reshape(k, k, order="F").copy())
+    for bf in bufs:
+        bf.release()
+    got = outs[0].astype(np.float64)
+    full = alpha * (a.astype(np.float64) @ b.astype(np.float64)) + beta * d.astype(np.float64) + gamma * np.eye(k)
+    want = np.triu(full) + np.triu(full, 1).T
+    assert np.array_equal(outs[0], outs[0].T)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_symm_gemm_engines_agree_and_no_d_term():
+    """No D term (d.len == 0), FP32-pipe engine vs tcgen05 engine on the same operands."""
+    L = capi.lib()
+    k = 256
+    rng = np.random.default_rng(7)
+    a, b = _sym32(rng, k), _sym32(rng, k)
+    ab, bb = capi.Buf(a.reshape(-1, order="F").copy(), mutable=False), capi.Buf(b.reshape(-1, order="F").copy(), mutable=False)
+    res = {}
+    for engine in (1, 2):
+        c = np.zeros(k * k, dtype=np.float32)
+        cb = capi.Buf(c)
+        capi.check(L.tb_symm_gemm_f32(k, 1.0, ab.view(), bb.view(), 0.0, capi.View(0, 0, 0), 0.0, cb.view(), engine, 0))
+        cb.release()
+        res[engine] = c.astype(np.float64)
+    ab.release(); bb.release()
+    assert np.abs(res[1] - res[2]).max() <= 3e-6 * np.abs(res[1]).max()
+    # an unaligned size is refused by the tensor-core engine, loudly
+    k2 = 30
+    a2 = _sym32(rng, k2).reshape(-1).copy()
+    x = capi.Buf(a2, mutable=False); y = capi.Buf(np.zeros(k2 * k2, dtype=np.float32))
+    assert L.tb_symm_gemm_f32(k2, 1.0, x.view(), x.view(), 0.0, capi.View(0, 0, 0), 0.0, y.view(), 2, 0) != 0
+    x.release(); y.release()
+
+
+@pytest.mark.parametrize("k", [64, 128, 132, 256])
+@pytest.mark.parametrize("path", [0, 2, 3])
+def test_proj_psd_tensor_core_paths_vs_oracle(k, path, request):
+    """ConePSD::proj in f32 through the tcgen05 sign iteration (0: split-K chosen, 3: no split-K) and the FP32-pipe
+    one (2), each against the oracle's dsyevr + dsyr restatement (f64lapack.rs:78-108)."""
+    capi.check(capi.lib().tb_set_psd_path(path))
+    request.addfinalizer(lambda: capi.check(capi.lib().tb_set_psd_path(0)))
+    rng = np.random.default_rng(k)
+    g = rng.standard_normal((k, k))
+    x = svec((g + g.T) / 2).astype(np.float32)
+    want = x.astype(np.float64).copy()
+    O.ConePSD(np.zeros(O.ConePSD.query_worklen(x.size)), 1e-12).proj(False, want)
+    xb, wb = capi.Buf(x), capi.Buf(np.zeros(2 * k * k + k, dtype=np.float32))
+    capi.check(capi.fn("tb_proj_psd", np.float32)(xb.view(), 1e-12, wb.view()))
+    xb.release(); wb.release()
+    assert np.abs(x - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (k, path)

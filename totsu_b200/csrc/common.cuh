@@ -150,7 +150,7 @@ struct Context {
     uint64_t buf_gen = 0;
     tb_handle last_lookup = 0;
     int gemv_mode = 0;
-    int psd_mode = 0;                    // 0: matrix-sign iteration (GEMM-only), 1: Jacobi eigendecomposition
+    int psd_mode = 0;                    // 0: matrix-sign iteration (tcgen05 GEMMs for f32), 1: Jacobi eigendecomposition, 2: sign on FP32/FP64 pipes, 3: tcgen05 without split-K
     char* eig_scratch = nullptr;         // 3 k*k matrices for the sign iteration
     size_t eig_scratch_bytes = 0;
     // event-pair profiling of the streaming matvec
@@ -260,6 +260,9 @@ void dist_check_fault();      // throws if a peer-exchange wait timed out
 
 // ---- eig internals (cone.cu calls into eig.cu for PSD blocks) -------------------------------------------
 template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len);
+// tcgen05 3xTF32 symmetric GEMM (psd_tc.cu): C = alpha*A*B + beta*D + gamma*I, all symmetric k x k column-major f32
+bool symm_gemm_tc_usable(const float* A, const float* B, const float* D, const float* C, size_t k);
+void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk);
 
 }  // namespace tb
 

@@ -329,8 +329,19 @@ __global__ void __launch_bounds__(SG_THREADS) symm_gemm_kernel(const T* __restri
     }
 }
 
+// engine: 0 = choose (tensor cores for f32 when the operands qualify), 1 = FP32/FP64-pipe kernel above, 2 = tcgen05 (psd_tc.cu)
 template <typename T>
-static void symm_gemm(const T* A, const T* B, const T* D, T* C, size_t k, T alpha, T beta, T gamma, const double* inv_norm_sq = nullptr) {
+static void symm_gemm(const T* A, const T* B, const T* D, T* C, size_t k, T alpha, T beta, T gamma, const double* inv_norm_sq = nullptr,
+                      int engine = 0, int splitk = 0) {
+    if constexpr (sizeof(T) == 4) {
+        if (engine == 2 || (engine == 0 && inv_norm_sq == nullptr && k >= 64 && symm_gemm_tc_usable(A, B, D, C, k))) {
+            TB_REQUIRE(inv_norm_sq == nullptr, "symm_gemm: the tensor-core engine takes alpha by value");
+            symm_gemm_tc(A, B, D, C, k, alpha, beta, gamma, splitk);
+            return;
+        }
+    } else {
+        TB_REQUIRE(engine != 2, "symm_gemm: the tensor-core engine is f32 only (no FP64 tensor path on sm_100a worth using)");
+    }
     const unsigned nt = (unsigned)((k + SG_TILE - 1) / SG_TILE);
     symm_gemm_kernel<T><<<dim3(nt, nt), SG_THREADS, 0, ctx().stream>>>(A, B, D, C, (int)k, alpha, beta, gamma, inv_norm_sq);
     TB_LAUNCH_CHECK();
@@ -372,18 +383,20 @@ template <typename T> static void psd_project_sign(T* x, size_t k, T* work) {
     const int n1 = sizeof(T) == 4 ? 10 : 24, n2 = sizeof(T) == 4 ? 8 : 12;
     const T qa = (T)3.4445, qb = (T)-4.7750, qc = (T)2.0315;
     T* S = S0; T* Sn = S1;
+    // psd_mode 0: tensor cores where they apply (f32, k >= 64, k % 4 == 0); 2: FP32/FP64-pipe GEMM; 3: tensor cores without split-K
+    const int eng = c.psd_mode == 2 ? 1 : 0, sk = c.psd_mode == 3 ? 1 : 0;
     for (int it = 0; it < n1; ++it) {
-        symm_gemm<T>(S, S, nullptr, T2, k, T(1), T(0), T(0));            // T2 = S^2
-        symm_gemm<T>(T2, T2, T2, P, k, qc, qb, qa);                     // P = c S^4 + b S^2 + a I
-        symm_gemm<T>(S, P, nullptr, Sn, k, T(1), T(0), T(0));           // S' = S P
+        symm_gemm<T>(S, S, nullptr, T2, k, T(1), T(0), T(0), nullptr, eng, sk);            // T2 = S^2
+        symm_gemm<T>(T2, T2, T2, P, k, qc, qb, qa, nullptr, eng, sk);                     // P = c S^4 + b S^2 + a I
+        symm_gemm<T>(S, P, nullptr, Sn, k, T(1), T(0), T(0), nullptr, eng, sk);           // S' = S P
         std::swap(S, Sn);
     }
     for (int it = 0; it < n2; ++it) {
-        symm_gemm<T>(S, S, nullptr, P, k, T(-0.5), T(0), T(1.5));       // P = 1.5 I - 0.5 S^2
-        symm_gemm<T>(S, P, nullptr, Sn, k, T(1), T(0), T(0));           // S' = S P
+        symm_gemm<T>(S, S, nullptr, P, k, T(-0.5), T(0), T(1.5), nullptr, eng, sk);       // P = 1.5 I - 0.5 S^2
+        symm_gemm<T>(S, P, nullptr, Sn, k, T(1), T(0), T(0), nullptr, eng, sk);           // S' = S P
         std::swap(S, Sn);
     }
-    symm_gemm<T>(X, S, X, P, k, T(0.5), T(0.5), T(0));                  // proj = (X S + X) / 2
+    symm_gemm<T>(X, S, X, P, k, T(0.5), T(0.5), T(0), nullptr, eng, sk);                  // proj = (X S + X) / 2
     pack_kernel<T><<<gkk, 256, 0, c.stream>>>(P, k, 1, T(1) / sq2, x);
     TB_LAUNCH_CHECK();
 }
@@ -394,7 +407,7 @@ template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, siz
     TB_REQUIRE(k * (k + 1) / 2 == sn, "ConePSD: length is not a triangular number");       // cone_psd.rs:35
     TB_REQUIRE(work_len >= 2 * k * k + k, "ConePSD: work shortage");                        // cone_psd.rs:58-61
     if (k == 0) return;
-    if (ctx().psd_mode == 0 && k > 1) {
+    if (ctx().psd_mode != 1 && k > 1) {
         psd_project_sign<T>(x, k, work);
         return;
     }
@@ -456,7 +469,8 @@ using namespace tb;
 extern "C" {
 int tb_set_psd_path(int mode) {
     return api([&] {
-        TB_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (matrix-sign iteration) or 1 (Jacobi eigendecomposition)");
+        TB_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0 (matrix-sign iteration, tcgen05 GEMMs for f32), 1 (Jacobi eigendecomposition), "
+                                           "2 (matrix-sign iteration on the FP32/FP64 pipes) or 3 (tcgen05 without split-K)");
         ctx().psd_mode = mode;
     });
 }
@@ -465,6 +479,18 @@ int tb_map_eig_begin_f32(tb_view m, int hs, float sd, float ez, tb_view w, float
 int tb_map_eig_begin_f64(tb_view m, int hs, double sd, double ez, tb_view w, double* e) { return api([&] { api_map_eig_begin<double>(m, hs, sd, ez, w, e); }); }
 int tb_map_eig_finish_f32(tb_view m, int hs, float sd, tb_view w, const float* ne, const uint8_t* k) { return api([&] { api_map_eig_finish<float>(m, hs, sd, w, ne, k); }); }
 int tb_map_eig_finish_f64(tb_view m, int hs, double sd, tb_view w, const double* ne, const uint8_t* k) { return api([&] { api_map_eig_finish<double>(m, hs, sd, w, ne, k); }); }
+int tb_symm_gemm_f32(size_t k, float alpha, tb_view a, tb_view b, float beta, tb_view d, float gamma, tb_view cv, int engine, int splitk) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(a.len == k * k && b.len == k * k && cv.len == k * k && (d.len == 0 || d.len == k * k), "symm_gemm: every matrix is k x k");
+        TB_REQUIRE(engine == 1 || engine == 2, "symm_gemm: engine is 1 (FP32 pipe) or 2 (tcgen05)");
+        const float* pa = rptr<float>(a);
+        const float* pb = rptr<float>(b);
+        const float* pd = d.len ? rptr<float>(d) : nullptr;
+        float* pc = wptr<float>(cv, true);
+        symm_gemm<float>(pa, pb, pd, pc, k, alpha, beta, gamma, nullptr, engine, splitk);
+    });
+}
 int tb_proj_psd_f32(tb_view x, float ez, tb_view w) { return api([&] { api_proj_psd<float>(x, ez, w); }); }
 int tb_proj_psd_f64(tb_view x, double ez, tb_view w) { return api([&] { api_proj_psd<double>(x, ez, w); }); }
 }

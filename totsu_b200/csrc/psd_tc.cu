@@ -1,0 +1,367 @@
+// Tensor-core engine of the ConePSD projection (totsu_core/src/cone_psd.rs:56-79; CPU twin
+// totsu_f64lapack/src/f64lapack.rs:78-108).  eig.cu computes proj_{S+}(X) = (X + X sign(X)) / 2 with a GEMM-only
+// polynomial iteration; every product in it is  C = alpha * A * B + beta * D + gamma * I  with A, B, D symmetric
+// k x k (f32, column-major) and C symmetric.  This file is that GEMM on the 5th-generation tensor cores:
+//
+//   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 128, K = 8 per instruction, accumulator in TMEM (128 columns);
+//   * fp32 accuracy from three TF32 products per K step ("3xTF32"):  A = Ah + Al, B = Bh + Bl with Ah = rna_tf32(A),
+//     Al = A - Ah (exact in fp32)  =>  A*B ~= Ah*Bh + Ah*Bl + Al*Bh, dropped term Al*Bl <= 2^-22 |A||B|;
+//   * both operands are K-major for free: B[l, j] is column j of the column-major array, and A[i, l] = A[l, i]
+//     (A symmetric) is column i - so a tile row is a contiguous run of K in global memory;
+//   * 8 producer warps read 128-byte row segments (L2-resident: the matrices are <= a few MB), split hi/lo in
+//     registers and store both into the canonical no-swizzle K-major core-matrix layout (8 rows x 16 B contiguous,
+//     LBO = 128 B along K, SBO = 1024 B along M/N), 3-stage mbarrier ring; one elected lane of warp 8 issues the MMAs
+//     and releases stages with tcgen05.commit;
+//   * split-K across a thread-block cluster (1,1,S): each CTA owns K/S of the reduction, parks its partial tile in
+//     its own shared memory, and after a cluster barrier CTA z sums rows [z*128/S, (z+1)*128/S) of all partials over
+//     DSMEM in rank order (fixed order: bit-reproducible, no atomics) and runs the epilogue for those rows;
+//   * epilogue keeps entries on or above the diagonal and mirrors them (through a padded smem transpose so both the
+//     direct and the mirrored stores are coalesced): iterates stay EXACTLY symmetric, which the sign iteration needs
+//     (eig.cu) and which makes the A-operand trick above legal for the next product.
+//
+// k = 512 (BASELINE config C4) gives only 10 upper 128 x 128 tiles, so the machine is far from full: split-K 4 brings
+// it to 40 CTAs; the kernel is bounded by shared-memory bandwidth (MMA operand reads + hi/lo stores) and launch
+// latency, not by the tensor pipe - DESIGN.md section 3.4 has the measured numbers.
+#include "common.cuh"
+
+namespace tb {
+namespace tc {
+
+constexpr int TM = 128, TN = 128, KC = 32, STAGES = 3;
+constexpr int PRODUCER_WARPS = 8;
+constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;
+constexpr int TILE_BYTES = TM * KC * 4;           // one operand half (hi or lo) of one stage: 16 KB
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
+constexpr int LBO = 128;                          // next core matrix along K
+constexpr int SBO = (KC / 4) * 128;               // next 8-row group along M/N: 1024 B
+constexpr int PAD = TM + 1;                       // padded leading dimension of the staging tiles
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
+constexpr int TMEM_COLS = 128;
+static_assert(TM == TN, "the staging tiles assume square tiles");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"((uint32_t)TMEM_COLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, TF32 inputs, fp32 accumulation
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread `lane` of the warp gets row (lane_base + lane), columns [col, col + 32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t rank) {
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute/arch/mma_sm100_desc.hpp SmemDescriptor layout):
+// start address >> 4 at [0,14), leading byte offset >> 4 at [16,30), stride byte offset >> 4 at [32,46), version 1 at [46,48)
+__host__ __device__ __forceinline__ uint64_t smem_desc_fields(uint32_t lbo, uint32_t sbo) {
+    return ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint64_t fields, uint32_t saddr) { return fields | (uint64_t)((saddr & 0x3FFFFu) >> 4); }
+// instruction descriptor (InstrDescriptor): c_format F32 = 1 at [4,6), a/b_format TF32 = 2 at [7,10)/[10,13),
+// a/b major K = 0 at 15/16, N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ void split_tf32(const float4& v, float4& hi, float4& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.x)); hi.x = __uint_as_float(h); lo.x = v.x - hi.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.y)); hi.y = __uint_as_float(h); lo.y = v.y - hi.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.z)); hi.z = __uint_as_float(h); lo.z = v.z - hi.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.w)); hi.w = __uint_as_float(h); lo.w = v.w - hi.w;
+}
+
+// C = alpha * (A * B) + beta * D + gamma * I; A, B, D symmetric k x k column-major, k % 4 == 0, 16-byte aligned.
+// grid = (upper tile pairs, 1, SPLITK), cluster (1, 1, SPLITK).
+template <int SPLITK>
+__global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ D,
+                                                                  float* __restrict__ C, int k, float alpha, float beta, float gamma, uint64_t dfields) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* accf = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // decode the upper tile pair (bi <= bj) from blockIdx.x: row bi holds nt - bi tiles
+    const int nt = (k + TM - 1) / TM;
+    int bi = 0, rem = blockIdx.x;
+    while (rem >= nt - bi) { rem -= nt - bi; ++bi; }
+    const int bj = bi + rem;
+    const int i0 = bi * TM, j0 = bj * TN;
+    const int z = SPLITK > 1 ? (int)cluster_rank() : 0;
+    const int nk = (k + KC - 1) / KC;
+    const int c0 = (int)((long long)z * nk / SPLITK), c1 = (int)((long long)(z + 1) * nk / SPLITK);
+    const int nmy = c1 - c0;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PRODUCER_WARPS * 32); mbar_init(&empty[s], 1); }
+        mbar_init(accf, 1);
+        mbar_fence_init();
+    }
+    if (warp == PRODUCER_WARPS) tmem_alloc(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < PRODUCER_WARPS) {
+        // ---- producers: global (L2) -> registers -> hi/lo split -> canonical K-major core matrices in smem
+        const int r8 = lane & 7, cq = lane >> 3;
+        for (int it = 0; it < nmy; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            const int l0 = (c0 + it) * KC;
+            uint8_t* st = smem + s * STAGE_BYTES;
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int u = warp + PRODUCER_WARPS * q;          // (row group, K half) unit: 16 x 2 per operand tile
+                const int row = (u >> 1) * 8 + r8, kk = l0 + ((u & 1) * 4 + cq) * 4;
+                const int gi = i0 + row, gj = j0 + row;
+                va[q] = (gi < k && kk < k) ? *reinterpret_cast<const float4*>(A + (size_t)gi * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[q] = (gj < k && kk < k) ? *reinterpret_cast<const float4*>(B + (size_t)gj * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int u = warp + PRODUCER_WARPS * q;
+                const int off = (u >> 1) * SBO + ((u & 1) * 4 + cq) * LBO + r8 * 16;
+                float4 hi, lo;
+                split_tf32(va[q], hi, lo);
+                *reinterpret_cast<float4*>(st + off) = hi;
+                *reinterpret_cast<float4*>(st + TILE_BYTES + off) = lo;
+                split_tf32(vb[q], hi, lo);
+                *reinterpret_cast<float4*>(st + 2 * TILE_BYTES + off) = hi;
+                *reinterpret_cast<float4*>(st + 3 * TILE_BYTES + off) = lo;
+            }
+            fence_async_shared();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            mbar_arrive(&full[s]);
+        }
+    } else {
+        // ---- MMA issuer: one lane, 3 TF32 products per K step of 8
+        for (int it = 0; it < nmy; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < KC / 8; ++ks) {
+                    const uint32_t o = (uint32_t)ks * 2u * LBO;
+                    const uint64_t ah = smem_desc(dfields, sa + o), al = smem_desc(dfields, sa + TILE_BYTES + o);
+                    const uint64_t bh = smem_desc(dfields, sa + 2 * TILE_BYTES + o), bl = smem_desc(dfields, sa + 3 * TILE_BYTES + o);
+                    mma_tf32(tmem_base, al, bh, IDESC, (it | ks) != 0 ? 1u : 0u);
+                    mma_tf32(tmem_base, ah, bl, IDESC, 1u);
+                    mma_tf32(tmem_base, ah, bh, IDESC, 1u);
+                }
+                mma_commit(&empty[s]);                       // stage reusable once these MMAs have read it
+                if (it == nmy - 1) mma_commit(accf);         // accumulator complete
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers (thread = tile row, registers = 32 consecutive columns)
+    float* stage0 = reinterpret_cast<float*>(smem);
+    float* Pt = stage0;                                              // [col][PAD] partial tile (split-K only)
+    float* Rt = SPLITK > 1 ? stage0 + TN * PAD : stage0;            // [row][PAD] finished values for the mirror pass
+    if (warp < PRODUCER_WARPS) {
+        const int quad = warp & 3, chalf = warp >> 2;
+        const int row = quad * 32 + lane;
+        if (nmy > 0) { mbar_wait(accf, 0u); tc_fence_after(); }
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            const int cbase = chalf * 64 + cc * 32;
+            float v[32];
+            if (nmy > 0) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)cbase, v);
+            else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = 0.f;
+            }
+            if (SPLITK > 1) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) Pt[(cbase + t) * PAD + row] = v[t];
+            } else {
+                const int gi = i0 + row;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int gj = j0 + cbase + t;
+                    float val = alpha * v[t];
+                    if (gi < k && gj < k && gi <= gj) {
+                        if (beta != 0.f) val += beta * D[(size_t)gj * k + gi];
+                        if (gi == gj) val += gamma;
+                        C[(size_t)gj * k + gi] = val;
+                    }
+                    Rt[row * PAD + cbase + t] = val;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    if (SPLITK > 1) {
+        cluster_sync_all();                 // every partial tile of the cluster is parked
+        constexpr int ROWS = TM / (SPLITK > 1 ? SPLITK : 1);
+        static_assert(ROWS >= 32 || SPLITK == 1, "a CTA reduces at least one warp-width of rows");
+        if (warp < PRODUCER_WARPS) {
+            for (int rr = 0; rr < ROWS; rr += 32) {
+                const int row = z * ROWS + rr + lane;
+                const int gi = i0 + row;
+                for (int j = warp; j < TN; j += PRODUCER_WARPS) {
+                    const uint32_t la = smem_u32(&Pt[j * PAD + row]);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int r = 0; r < SPLITK; ++r) acc += ld_dsmem(la, (uint32_t)r);
+                    const int gj = j0 + j;
+                    float val = alpha * acc;
+                    if (gi < k && gj < k && gi <= gj) {
+                        if (beta != 0.f) val += beta * D[(size_t)gj * k + gi];
+                        if (gi == gj) val += gamma;
+                        C[(size_t)gj * k + gi] = val;
+                    }
+                    Rt[(rr + lane) * PAD + j] = val;
+                }
+            }
+        }
+        __syncthreads();
+        if (warp < PRODUCER_WARPS) {
+            for (int i = warp; i < ROWS; i += PRODUCER_WARPS) {
+                const int gi = i0 + z * ROWS + i;
+                for (int jj = lane; jj < TN; jj += 32) {
+                    const int gj = j0 + jj;
+                    if (gi < k && gj < k && gi < gj) C[(size_t)gi * k + gj] = Rt[i * PAD + jj];
+                }
+            }
+        }
+        cluster_sync_all();                 // nobody leaves while a peer may still read its partial tile
+    } else {
+        __syncthreads();
+        if (warp < PRODUCER_WARPS) {
+            for (int i = warp; i < TM; i += PRODUCER_WARPS) {
+                const int gi = i0 + i;
+                for (int jj = lane; jj < TN; jj += 32) {
+                    const int gj = j0 + jj;
+                    if (gi < k && gj < k && gi < gj) C[(size_t)gi * k + gj] = Rt[i * PAD + jj];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    tc_fence_after();
+    if (warp == PRODUCER_WARPS) tmem_dealloc(tmem_base);
+}
+
+template <int SPLITK> static void launch(const float* A, const float* B, const float* D, float* C, int k, float alpha, float beta, float gamma) {
+    static bool configured = false;
+    auto kern = symm_gemm_tc_kernel<SPLITK>;
+    if (!configured) {
+        TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int nt = (k + TM - 1) / TM;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(nt * (nt + 1) / 2), 1, SPLITK);
+    cfg.blockDim = dim3(THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = ctx().stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = SPLITK;
+    cfg.attrs = attr;
+    cfg.numAttrs = SPLITK > 1 ? 1 : 0;
+    // TB_TC_DESC_SWAP=1 (debug) exchanges the leading/stride byte offsets of the operand descriptors
+    static const bool swap = [] { const char* e = getenv("TB_TC_DESC_SWAP"); return e && e[0] == '1'; }();
+    const uint64_t dfields = swap ? smem_desc_fields(SBO, LBO) : smem_desc_fields(LBO, SBO);
+    TB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, B, D, C, k, alpha, beta, gamma, dfields));
+    count_launch();
+}
+
+}  // namespace tc
+
+bool symm_gemm_tc_usable(const float* A, const float* B, const float* D, const float* C, size_t k) {
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return k >= 4 && k % 4 == 0 && k <= 32768 && al(A) && al(B) && al(C) && (D == nullptr || al(D));
+}
+
+// splitk: 0 = choose, else 1 / 2 / 4
+void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk) {
+    TB_REQUIRE(symm_gemm_tc_usable(A, B, D, C, k), "tensor-core symmetric GEMM needs k % 4 == 0 and 16-byte aligned matrices");
+    TB_REQUIRE(C != A && C != B && C != D, "symm_gemm: the output must not alias an input");
+    if (splitk == 0) {
+        // enough CTAs to occupy the machine, at least two K chunks per CTA
+        const size_t nt = (k + tc::TM - 1) / tc::TM, pairs = nt * (nt + 1) / 2, nk = (k + tc::KC - 1) / tc::KC;
+        splitk = 1;
+        while (splitk < 4 && pairs * (size_t)splitk * 2 <= (size_t)ctx().sm_count && nk / (size_t)(splitk * 2) >= 2) splitk *= 2;
+    }
+    switch (splitk) {
+        case 1: tc::launch<1>(A, B, D, C, (int)k, alpha, beta, gamma); break;
+        case 2: tc::launch<2>(A, B, D, C, (int)k, alpha, beta, gamma); break;
+        case 4: tc::launch<4>(A, B, D, C, (int)k, alpha, beta, gamma); break;
+        default: fail(TB_ERR_ARG, "symm_gemm_tc: splitk must be 0, 1, 2 or 4");
+    }
+}
+
+}  // namespace tb
