@@ -134,7 +134,7 @@ int tb_map_eig_finish_f64(tb_view mat, int has_scale, double scale_diag, tb_view
 int tb_set_psd_path(int mode);
 /* The GEMM every step of the sign iteration is made of: C = alpha*A*B + beta*D + gamma*I with A, B, D symmetric k x k
  * column-major (d.len == 0: no D term), C symmetric (upper triangle computed, mirrored).  engine 2 = tcgen05 3xTF32
- * tensor-core kernel with split-K over a thread-block cluster (splitk 0 = choose, 1, 2 or 4; k % 4 == 0);
+ * tensor-core kernel with split-K over a thread-block cluster (splitk 0 = choose, 1, 2, 4 or 8; k % 4 == 0);
  * engine 1 = FP32-pipe kernel.  f32 only (f64 stays on the FP64 pipe).  Replaces the dsyr rank-1 loop of
  * f64lapack.rs:96-105 / the cublasSsyr loop of f32cuda.rs:316-324 inside ConePSD::proj; exported for the parity tests
  * and the tensor-pipe measurement of config C4.  tb_set_psd_path: 0 = sign iteration (tcgen05 for f32), 1 = Jacobi,

@@ -27,7 +27,7 @@
 namespace tb {
 namespace tc {
 
-constexpr int TM = 128, TN = 128, KC = 32, STAGES = 3;
+constexpr int TM = 128, TN = 128, KC = 32;
 constexpr int PRODUCER_WARPS = 8;
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;
 constexpr int TILE_BYTES = TM * KC * 4;           // one operand half (hi or lo) of one stage: 16 KB
@@ -35,7 +35,6 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
 constexpr int LBO = 128;                          // next core matrix along K
 constexpr int SBO = (KC / 4) * 128;               // next 8-row group along M/N: 1024 B
 constexpr int PAD = TM + 1;                       // padded leading dimension of the staging tiles
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128;
 constexpr int TMEM_COLS = 128;
 static_assert(TM == TN, "the staging tiles assume square tiles");
 
@@ -131,13 +130,39 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& hi, float4& 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.w)); hi.w = __uint_as_float(h); lo.w = v.w - hi.w;
 }
 
+__device__ __forceinline__ void st_dsmem(uint32_t remote_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// programmatic dependent launch: everything before pdl_wait() overlaps the tail of the previous kernel in the stream
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int SPLITK> struct Cfg {
+    static constexpr int STAGES = SPLITK > 1 ? 2 : 3;             // + one chunk in flight in registers
+    static constexpr int ROWS = TM / SPLITK;                      // tile rows this CTA finishes after the split-K exchange
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int INBOX_BYTES = SPLITK > 1 ? SPLITK * TN * ROWS * 4 : 0;   // [source rank][column][ROWS]: 64 KB
+    static constexpr int SMEM = PIPE_BYTES + INBOX_BYTES + 128;
+    static_assert(ROWS * PAD * 4 <= PIPE_BYTES, "the mirror staging tile reuses the pipeline buffers");
+};
+
 // C = alpha * (A * B) + beta * D + gamma * I; A, B, D symmetric k x k column-major, k % 4 == 0, 16-byte aligned.
 // grid = (upper tile pairs, 1, SPLITK), cluster (1, 1, SPLITK).
 template <int SPLITK>
 __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ D,
                                                                   float* __restrict__ C, int k, float alpha, float beta, float gamma, uint64_t dfields) {
+    using G = Cfg<SPLITK>;
+    constexpr int STAGES = G::STAGES, ROWS = G::ROWS;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    float* inbox = reinterpret_cast<float*>(smem + G::PIPE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::PIPE_BYTES + G::INBOX_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* accf = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
@@ -164,42 +189,51 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (SPLITK > 1) cluster_arrive();      // "I have started": matched by cluster_wait() before the first remote store
+    pdl_wait();                            // the producing kernel's stores are visible from here on
+    pdl_launch_dependents();               // the next kernel may run its prologue while this one works
 
     if (warp < PRODUCER_WARPS) {
         // ---- producers: global (L2) -> registers -> hi/lo split -> canonical K-major core matrices in smem
         const int r8 = lane & 7, cq = lane >> 3;
-        for (int it = 0; it < nmy; ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(&empty[s], ph ^ 1u);
-            const int l0 = (c0 + it) * KC;
-            uint8_t* st = smem + s * STAGE_BYTES;
-            float4 va[4], vb[4];
+        auto load = [&](int chunk, float4* v) {
+            const int l0 = chunk * KC;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int u = warp + PRODUCER_WARPS * q;          // (row group, K half) unit: 16 x 2 per operand tile
                 const int row = (u >> 1) * 8 + r8, kk = l0 + ((u & 1) * 4 + cq) * 4;
                 const int gi = i0 + row, gj = j0 + row;
-                va[q] = (gi < k && kk < k) ? *reinterpret_cast<const float4*>(A + (size_t)gi * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[q] = (gj < k && kk < k) ? *reinterpret_cast<const float4*>(B + (size_t)gj * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[q] = (gi < k && kk < k) ? *reinterpret_cast<const float4*>(A + (size_t)gi * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 + q] = (gj < k && kk < k) ? *reinterpret_cast<const float4*>(B + (size_t)gj * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        float4 cur[8], nxt[8];
+        if (nmy > 0) load(c0, cur);
+        for (int it = 0; it < nmy; ++it) {
+            if (it + 1 < nmy) load(c0 + it + 1, nxt);            // next chunk's loads fly while this one is split and stored
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int u = warp + PRODUCER_WARPS * q;
                 const int off = (u >> 1) * SBO + ((u & 1) * 4 + cq) * LBO + r8 * 16;
                 float4 hi, lo;
-                split_tf32(va[q], hi, lo);
+                split_tf32(cur[q], hi, lo);
                 *reinterpret_cast<float4*>(st + off) = hi;
                 *reinterpret_cast<float4*>(st + TILE_BYTES + off) = lo;
-                split_tf32(vb[q], hi, lo);
+                split_tf32(cur[4 + q], hi, lo);
                 *reinterpret_cast<float4*>(st + 2 * TILE_BYTES + off) = hi;
                 *reinterpret_cast<float4*>(st + 3 * TILE_BYTES + off) = lo;
             }
             fence_async_shared();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
             mbar_arrive(&full[s]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
         }
     } else {
-        // ---- MMA issuer: one lane, 3 TF32 products per K step of 8
+        // ---- MMA issuer: one lane, 3 TF32 products per K step of 8 (small terms first)
         for (int it = 0; it < nmy; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -224,9 +258,8 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     }
 
     // ---- epilogue: TMEM -> registers (thread = tile row, registers = 32 consecutive columns)
-    float* stage0 = reinterpret_cast<float*>(smem);
-    float* Pt = stage0;                                              // [col][PAD] partial tile (split-K only)
-    float* Rt = SPLITK > 1 ? stage0 + TN * PAD : stage0;            // [row][PAD] finished values for the mirror pass
+    float* Rt = reinterpret_cast<float*>(smem);     // [row][PAD] finished values for the mirror pass (the pipeline is drained by then)
+    if (SPLITK > 1) cluster_wait();                 // every CTA of the cluster runs: its inbox may be written
     if (warp < PRODUCER_WARPS) {
         const int quad = warp & 3, chalf = warp >> 2;
         const int row = quad * 32 + lane;
@@ -241,8 +274,11 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
                 for (int t = 0; t < 32; ++t) v[t] = 0.f;
             }
             if (SPLITK > 1) {
+                // push this row's partial sums into the inbox of the CTA that finishes the row: slot [z][col][row % ROWS]
+                const uint32_t la = smem_u32(&inbox[((size_t)z * TN + cbase) * ROWS + (row % ROWS)]);
+                const uint32_t ra = map_to_rank(la, (uint32_t)(row / ROWS));
 #pragma unroll
-                for (int t = 0; t < 32; ++t) Pt[(cbase + t) * PAD + row] = v[t];
+                for (int t = 0; t < 32; ++t) st_dsmem(ra + (uint32_t)(t * ROWS * 4), v[t]);
             } else {
                 const int gi = i0 + row;
 #pragma unroll
@@ -261,79 +297,79 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     }
     tc_fence_before();
     if (SPLITK > 1) {
-        cluster_sync_all();                 // every partial tile of the cluster is parked
-        constexpr int ROWS = TM / (SPLITK > 1 ? SPLITK : 1);
-        static_assert(ROWS >= 32 || SPLITK == 1, "a CTA reduces at least one warp-width of rows");
+        cluster_arrive();
+        cluster_wait();                     // all partial sums have landed; nothing remote is touched after this point
         if (warp < PRODUCER_WARPS) {
-            for (int rr = 0; rr < ROWS; rr += 32) {
-                const int row = z * ROWS + rr + lane;
-                const int gi = i0 + row;
-                for (int j = warp; j < TN; j += PRODUCER_WARPS) {
-                    const uint32_t la = smem_u32(&Pt[j * PAD + row]);
-                    float acc = 0.f;
+            for (int idx = tid; idx < TN * ROWS; idx += PRODUCER_WARPS * 32) {
+                const int i = idx % ROWS, j = idx / ROWS;
+                float acc = 0.f;
 #pragma unroll
-                    for (int r = 0; r < SPLITK; ++r) acc += ld_dsmem(la, (uint32_t)r);
-                    const int gj = j0 + j;
-                    float val = alpha * acc;
-                    if (gi < k && gj < k && gi <= gj) {
-                        if (beta != 0.f) val += beta * D[(size_t)gj * k + gi];
-                        if (gi == gj) val += gamma;
-                        C[(size_t)gj * k + gi] = val;
-                    }
-                    Rt[(rr + lane) * PAD + j] = val;
+                for (int r = 0; r < SPLITK; ++r) acc += inbox[r * TN * ROWS + idx];       // rank order: bit-reproducible
+                const int gi = i0 + z * ROWS + i, gj = j0 + j;
+                float val = alpha * acc;
+                if (gi < k && gj < k && gi <= gj) {
+                    if (beta != 0.f) val += beta * D[(size_t)gj * k + gi];
+                    if (gi == gj) val += gamma;
+                    C[(size_t)gj * k + gi] = val;
                 }
+                Rt[i * PAD + j] = val;
             }
         }
-        __syncthreads();
-        if (warp < PRODUCER_WARPS) {
-            for (int i = warp; i < ROWS; i += PRODUCER_WARPS) {
-                const int gi = i0 + z * ROWS + i;
-                for (int jj = lane; jj < TN; jj += 32) {
-                    const int gj = j0 + jj;
-                    if (gi < k && gj < k && gi < gj) C[(size_t)gi * k + gj] = Rt[i * PAD + jj];
-                }
-            }
-        }
-        cluster_sync_all();                 // nobody leaves while a peer may still read its partial tile
-    } else {
-        __syncthreads();
-        if (warp < PRODUCER_WARPS) {
-            for (int i = warp; i < TM; i += PRODUCER_WARPS) {
-                const int gi = i0 + i;
-                for (int jj = lane; jj < TN; jj += 32) {
-                    const int gj = j0 + jj;
-                    if (gi < k && gj < k && gi < gj) C[(size_t)gi * k + gj] = Rt[i * PAD + jj];
-                }
-            }
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    if (warp < PRODUCER_WARPS) {
+        // mirror: rows of the finished block become columns of C below the diagonal (coalesced along j)
+        for (int i = warp; i < ROWS; i += PRODUCER_WARPS) {
+            const int gi = i0 + z * ROWS + i;
+            for (int jj = lane; jj < TN; jj += 32) {
+                const int gj = j0 + jj;
+                if (gi < k && gj < k && gi < gj) C[(size_t)gi * k + gj] = Rt[i * PAD + jj];
+            }
+        }
+    }
+    __syncthreads();
     tc_fence_after();
     if (warp == PRODUCER_WARPS) tmem_dealloc(tmem_base);
+}
+
+static bool env_flag(const char* name, bool dflt) {
+    const char* e = getenv(name);
+    return e ? e[0] != '0' : dflt;
 }
 
 template <int SPLITK> static void launch(const float* A, const float* B, const float* D, float* C, int k, float alpha, float beta, float gamma) {
     static bool configured = false;
     auto kern = symm_gemm_tc_kernel<SPLITK>;
     if (!configured) {
-        TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<SPLITK>::SMEM));
         configured = true;
     }
     const int nt = (k + TM - 1) / TM;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(nt * (nt + 1) / 2), 1, SPLITK);
     cfg.blockDim = dim3(THREADS, 1, 1);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = Cfg<SPLITK>::SMEM;
     cfg.stream = ctx().stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = SPLITK;
+    cudaLaunchAttribute attr[2];
+    unsigned na = 0;
+    if (SPLITK > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = SPLITK;
+        ++na;
+    }
+    // TB_TC_PDL=0 turns programmatic dependent launch off (A/B measurement)
+    static const bool pdl = env_flag("TB_TC_PDL", true);
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = SPLITK > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     // TB_TC_DESC_SWAP=1 (debug) exchanges the leading/stride byte offsets of the operand descriptors
-    static const bool swap = [] { const char* e = getenv("TB_TC_DESC_SWAP"); return e && e[0] == '1'; }();
+    static const bool swap = env_flag("TB_TC_DESC_SWAP", false);
     const uint64_t dfields = swap ? smem_desc_fields(SBO, LBO) : smem_desc_fields(LBO, SBO);
     TB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, B, D, C, k, alpha, beta, gamma, dfields));
     count_launch();
@@ -353,14 +389,16 @@ void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size
     if (splitk == 0) {
         // enough CTAs to occupy the machine, at least two K chunks per CTA
         const size_t nt = (k + tc::TM - 1) / tc::TM, pairs = nt * (nt + 1) / 2, nk = (k + tc::KC - 1) / tc::KC;
+        static const int cap = [] { const char* e = getenv("TB_TC_MAX_SPLITK"); return e ? atoi(e) : 8; }();
         splitk = 1;
-        while (splitk < 4 && pairs * (size_t)splitk * 2 <= (size_t)ctx().sm_count && nk / (size_t)(splitk * 2) >= 2) splitk *= 2;
+        while (splitk < cap && pairs * (size_t)splitk * 2 <= (size_t)ctx().sm_count && nk / (size_t)(splitk * 2) >= 2) splitk *= 2;
     }
     switch (splitk) {
         case 1: tc::launch<1>(A, B, D, C, (int)k, alpha, beta, gamma); break;
         case 2: tc::launch<2>(A, B, D, C, (int)k, alpha, beta, gamma); break;
         case 4: tc::launch<4>(A, B, D, C, (int)k, alpha, beta, gamma); break;
-        default: fail(TB_ERR_ARG, "symm_gemm_tc: splitk must be 0, 1, 2 or 4");
+        case 8: tc::launch<8>(A, B, D, C, (int)k, alpha, beta, gamma); break;
+        default: fail(TB_ERR_ARG, "symm_gemm_tc: splitk must be 0, 1, 2, 4 or 8");
     }
 }
 
