@@ -12,16 +12,20 @@
 //     registers and store both into the canonical no-swizzle K-major core-matrix layout (8 rows x 16 B contiguous,
 //     LBO = 128 B along K, SBO = 1024 B along M/N), 3-stage mbarrier ring; one elected lane of warp 8 issues the MMAs
 //     and releases stages with tcgen05.commit;
-//   * split-K across a thread-block cluster (1,1,S): each CTA owns K/S of the reduction, parks its partial tile in
-//     its own shared memory, and after a cluster barrier CTA z sums rows [z*128/S, (z+1)*128/S) of all partials over
-//     DSMEM in rank order (fixed order: bit-reproducible, no atomics) and runs the epilogue for those rows;
+//   * split-K across a thread-block cluster (1,1,S), S <= 8: each CTA owns K/S of the reduction; from TMEM it PUSHES
+//     (st.shared::cluster) the rows [z'*128/S, (z'+1)*128/S) of its partial tile into the inbox of CTA z', and after one
+//     cluster barrier every CTA sums the S partials of its own rows from local shared memory in rank order (fixed
+//     order: bit-reproducible, no atomics) and runs the epilogue for them - stores are fire-and-forget, nothing waits
+//     on a remote load;
+//   * launched with programmatic stream serialization: barrier init + TMEM allocation of GEMM n+1 overlap the tail of
+//     GEMM n (griddepcontrol.wait before the first dependent access);
 //   * epilogue keeps entries on or above the diagonal and mirrors them (through a padded smem transpose so both the
 //     direct and the mirrored stores are coalesced): iterates stay EXACTLY symmetric, which the sign iteration needs
 //     (eig.cu) and which makes the A-operand trick above legal for the next product.
 //
-// k = 512 (BASELINE config C4) gives only 10 upper 128 x 128 tiles, so the machine is far from full: split-K 4 brings
-// it to 40 CTAs; the kernel is bounded by shared-memory bandwidth (MMA operand reads + hi/lo stores) and launch
-// latency, not by the tensor pipe - DESIGN.md section 3.4 has the measured numbers.
+// k = 512 (BASELINE config C4) gives only 10 upper 128 x 128 tiles, so the machine is far from full: split-K 8 brings
+// it to 80 CTAs of 2 K-chunks each; the GEMM is then bounded by fixed latencies (launch, L2 round trip, cluster
+// barrier, epilogue), not by the tensor pipe - DESIGN.md section 3.4 has the measured numbers.
 #include "common.cuh"
 
 namespace tb {
@@ -122,12 +126,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint64_t fields, uint32_t saddr) {
 // a/b major K = 0 at 15/16, N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
+// hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa to the magnitude, clear the low 13
+// bits - what cvt.rna.tf32.f32 computes, without the NaN/Inf branch ptxas emits for it), lo = x - hi (exact)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_tf32(const float4& v, float4& hi, float4& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.x)); hi.x = __uint_as_float(h); lo.x = v.x - hi.x;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.y)); hi.y = __uint_as_float(h); lo.y = v.y - hi.y;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.z)); hi.z = __uint_as_float(h); lo.z = v.z - hi.z;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v.w)); hi.w = __uint_as_float(h); lo.w = v.w - hi.w;
+    hi.x = tf32_hi(v.x); lo.x = v.x - hi.x;
+    hi.y = tf32_hi(v.y); lo.y = v.y - hi.y;
+    hi.z = tf32_hi(v.z); lo.z = v.z - hi.z;
+    hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
 }
 
 __device__ __forceinline__ void st_dsmem(uint32_t remote_addr, float v) {
