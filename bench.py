@@ -27,15 +27,33 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# cone: ("soc", n_blocks, block_dim) | ("rpos", m) | ("psd", k).  kind "dense": one stacked dense A (fused DenseOp +
+# ProductCone route); kind "qp": the ProbQP front-end (stock MatOp route: packed P^(1/2) via transform_sp + G, A_eq via
+# transform_ge; cone RotSOC(n+2) x RPos(m) x Zero(p), qp.rs:325-338).
 WORKLOADS = {
-    # name: (n_blocks, block_dim, n)          m = n_blocks * block_dim; block_dim == 1: ConeRPos(m) (an LP)
-    "c3_socp_1024x64_A65536x16384": (1024, 64, 16384),
-    "socp_small_128x64_A8192x4096": (128, 64, 4096),
-    "c5_lp_A262144x65536": (262144, 1, 65536),          # BASELINE config C5: 68.7 GB of A (f32), meant for 8 GPUs
-    "lp_A32768x65536": (32768, 1, 65536),               # one C5 shard on one GPU
+    "c3_socp_1024x64_A65536x16384": {"kind": "dense", "cone": ("soc", 1024, 64), "n": 16384},       # BASELINE config C3 (the headline)
+    "socp_small_128x64_A8192x4096": {"kind": "dense", "cone": ("soc", 128, 64), "n": 4096},
+    "c5_lp_A262144x65536": {"kind": "dense", "cone": ("rpos", 262144), "n": 65536},                  # C5: 68.7 GB of A (f32), meant for 8 GPUs
+    "lp_A32768x65536": {"kind": "dense", "cone": ("rpos", 32768), "n": 65536},                       # one C5 shard on one GPU
+    "c4_sdp_psd512_A131328x1024": {"kind": "dense", "cone": ("psd", 512), "n": 1024},                # C4: one ConePSD block 512 x 512
+    "sdp_small_psd64_A2080x128": {"kind": "dense", "cone": ("psd", 64), "n": 128},
+    "c2_qp_n8192_m8192_p1024": {"kind": "qp", "n": 8192, "m": 8192, "p": 1024},                      # C2: A is 17410 x 8193 through ProbQP
+    "qp_small_n512_m512_p64": {"kind": "qp", "n": 512, "m": 512, "p": 64},
 }
 DEFAULT_WORKLOAD = "c3_socp_1024x64_A65536x16384"
 SEED = 0
+
+
+def cone_rows(cone):
+    return cone[1] * cone[2] if cone[0] == "soc" else cone[1] if cone[0] == "rpos" else cone[1] * (cone[1] + 1) // 2
+
+
+def cone_text(cone):
+    if cone[0] == "soc":
+        return "%d x ConeSOC(%d)" % (cone[1], cone[2])
+    if cone[0] == "rpos":
+        return "ConeRPos(%d)" % cone[1]
+    return "ConePSD(%d x %d, sk = %d)" % (cone[1], cone[1], cone_rows(cone))
 
 
 def measured_peaks():
@@ -47,20 +65,53 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------------------
-def instance_vectors(nblk, bdim, n, seed):
-    """x0, s0 in int K, y0 in int K* for the feasible-by-construction recipe (SURVEY.md §8d)."""
+def svec(mat):
+    """Symmetric matrix -> packed upper triangle by columns, off-diagonals scaled by sqrt(2) (cone_psd.rs:18)."""
+    k = mat.shape[0]
+    r, c = np.triu_indices(k)
+    order = np.lexsort((r, c))                     # by column, then row: index c(c+1)/2 + r
+    r, c = r[order], c[order]
+    return mat[r, c] * np.where(r == c, 1.0, math.sqrt(2.0))
+
+
+def instance_vectors(cone, n, seed):
+    """x0, s0 in int K, y0 in int K* for the feasible-by-construction recipe (SURVEY.md 8d)."""
     rng = np.random.default_rng(seed + 12345)
-    m = nblk * bdim
+    m = cone_rows(cone)
     sc = 1.0 / math.sqrt(m)        # keeps ||b||, ||c|| = O(1): tau stays > 0 and criteria_conv runs every iteration
     x0 = rng.standard_normal(n) * sc
 
     def interior():
-        if bdim == 1:
+        if cone[0] == "rpos":
             return (np.abs(rng.standard_normal(m)) + 0.1) * sc
-        v = rng.standard_normal((nblk, bdim))
-        v[:, 0] = np.linalg.norm(v[:, 1:], axis=1) + 1.0
-        return v.reshape(m) * sc
+        if cone[0] == "soc":
+            v = rng.standard_normal((cone[1], cone[2]))
+            v[:, 0] = np.linalg.norm(v[:, 1:], axis=1) + 1.0
+            return v.reshape(m) * sc
+        k = cone[1]
+        g = rng.standard_normal((k, k))
+        return svec(g.T @ g / k + np.eye(k)) * sc
     return x0, interior(), interior()
+
+
+def qp_instance(n, m, p, dt):
+    """ProbQP data of the benchmark_qp shape (experimental/benchmark_qp/src/main.rs:14-54) plus p equality rows:
+    diagonal P ~ U(0,1) (so P^(1/2) is known in closed form), G, A_eq ~ U(-1,1)/sqrt(n) from the counter-based
+    generator, h = G x0 + slack, b = A_eq x0: feasible and bounded.  Matrices are returned flat column-major."""
+    from totsu_b200 import synth
+    rng = np.random.default_rng(SEED + 777)
+    scale = dt(1.0 / math.sqrt(n))
+    g = synth.uniform_matrix(m, n, SEED, scale, dtype=dt)
+    a = synth.uniform_matrix(p, n, SEED + 1, scale, dtype=dt)
+    x0 = rng.standard_normal(n) / math.sqrt(n)
+    h = (g.astype(np.float64) @ x0 + np.abs(rng.standard_normal(m)) * 0.1 + 0.01).astype(dt)
+    b = (a.astype(np.float64) @ x0).astype(dt)
+    q = (rng.standard_normal(n) / math.sqrt(n)).astype(dt)
+    pdiag = rng.uniform(0.05, 1.0, n)
+    psqrt = np.zeros(n * (n + 1) // 2, dtype=dt)
+    idx = np.arange(n, dtype=np.int64)
+    psqrt[idx * (idx + 1) // 2 + idx] = np.sqrt(pdiag).astype(dt)
+    return psqrt, q, g.reshape(-1, order="F"), h, a.reshape(-1, order="F"), b
 
 
 class Clocks:
@@ -105,20 +156,52 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_leg(nblk, bdim, n, steps, warmup, sample_blocks=None, threads=None):
-    """The reference's CPU path for this workload: the oracle's port of ProbSOCP + F64LAPACK (per-block dgemv, f64,
-    OpenBLAS instead of MKL) on a bounded row sample of the same A (the first `sample_blocks` cone blocks), timed
-    per iteration and scaled linearly in rows (the iteration is dgemv-bound)."""
+def cpu_reference_leg(spec, steps, warmup, sample_blocks=None, threads=None):
+    """The reference's CPU path for this workload: the oracle's port of the matching front-end + F64LAPACK (f64,
+    OpenBLAS instead of MKL).  SOCP / LP: a bounded row sample of the same A (the first `sample_blocks` cone blocks),
+    timed per iteration and scaled linearly in rows (the iteration is dgemv-bound).  SDP and QP: the full workload
+    (a PSD block cannot be row-sampled; the QP fits)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import totsu_oracle as O
     from totsu_b200 import synth
     cores = threads or os.cpu_count() or 1
+    if spec["kind"] == "qp":
+        n, m, p = spec["n"], spec["m"], spec["p"]
+        psqrt, q, g, h, a, b = qp_instance(n, m, p, np.float32)
+        f8 = lambda v: np.asarray(v, dtype=np.float64)
+        prob = O.ProbQP(O.MatBuild(O.MatType.SymPack(n), f8(psqrt)), O.MatBuild(O.MatType.General(n, 1), f8(q)),
+                        O.MatBuild(O.MatType.General(m, n), f8(g)), O.MatBuild(O.MatType.General(m, 1), f8(h)),
+                        O.MatBuild(O.MatType.General(p, n), f8(a)), O.MatBuild(O.MatType.General(p, 1), f8(b)), 1e-12, p_is_sqrt=True)
+        del g, a, psqrt
+        return _time_oracle(O, prob, steps, warmup, cores, 1.0,
+                            "the full workload (f64; dspmv on the packed P^(1/2) + dgemv on G and A_eq like ProbQP, OpenBLAS via numpy/scipy instead of MKL)")
+    cone, n = spec["cone"], spec["n"]
+    m = cone_rows(cone)
+    scale = np.float32(1.0 / math.sqrt(n))
+    x0, s0, y0 = instance_vectors(cone, n, SEED)
+    if cone[0] == "psd":
+        k = cone[1]
+        a = np.empty((m, n), dtype=np.float64, order="F")
+        for c0 in range(0, n, 128):          # column panels keep the generator's temporaries small
+            a[:, c0:c0 + 128] = synth.uniform_matrix(m, min(128, n - c0), SEED, scale, dtype=np.float32, cols=np.arange(c0, min(n, c0 + 128)))
+        b = (a @ x0 + s0).astype(np.float32).astype(np.float64)
+        c = (-(a.T @ y0)).astype(np.float32).astype(np.float64)
+
+        class _Dense:      # ProbSDP's operator tuple with p = 0 (sdp.rs:75-97: one MatOp symmat_f, sk x n) over the same A
+            def problem(self):
+                op_c = O.MatOp(O.MatType.General(n, 1), c)
+                op_a = O.MatOp(O.MatType.General(m, n), a.reshape(-1, order="F"))
+                op_b = O.MatOp(O.MatType.General(m, 1), b)
+                cone_o = O._ProductCone([(O.ConePSD(np.zeros(O.ConePSD.query_worklen(m)), 1e-12), m)])
+                return op_c, op_a, op_b, cone_o, np.zeros(O.Solver.query_worklen((m, n)))
+        return _time_oracle(O, _Dense(), steps, warmup, cores, 1.0,
+                            "the full workload (f64; one dgemv per op like ProbSDP's symmat_f, ConePSD::proj = LAPACK dsyevr + dsyr loop "
+                            "on %d x %d, OpenBLAS via numpy/scipy instead of MKL)" % (k, k))
+    nblk, bdim = (cone[1], cone[2]) if cone[0] == "soc" else (cone[1], 1)
     if sample_blocks is None:
         sample_blocks = max(1, min(nblk, 64 if bdim > 1 else 2048))
     ms = sample_blocks * bdim
-    scale = np.float32(1.0 / math.sqrt(n))
     a32 = synth.uniform_matrix(ms, n, SEED, scale, dtype=np.float32)
-    x0, s0, y0 = instance_vectors(nblk, bdim, n, SEED)
     a = a32.astype(np.float64)
     b = (a @ x0 + s0[:ms]).astype(np.float32).astype(np.float64)
     c = (-(a.T @ y0[:ms])).astype(np.float32).astype(np.float64)
@@ -186,17 +269,31 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    nblk, bdim, n = WORKLOADS[args.workload]
-    m = nblk * bdim
+    spec = WORKLOADS[args.workload]
+    is_qp = spec["kind"] == "qp"
+    esize = 4 if args.dtype == "f32" else 8
+    if is_qp:
+        qn, qm, qp_ = spec["n"], spec["m"], spec["p"]
+        m, n = (2 + qn) + qm + qp_, qn + 1                   # the stacked operator ProbQP builds (qp.rs:325-331)
+        dense_elems = qm * qn + qp_ * qn + qn * (qn + 1) // 2     # G + A_eq + packed P^(1/2): what one op / trans_op reads
+        config = {"workload": args.workload, "cone": "ConeRotSOC(%d) x ConeRPos(%d) x ConeZero(%d)" % (qn + 2, qm, qp_),
+                  "A": "%d x %d through ProbQP: G %d x %d + A_eq %d x %d dense column-major, P^(1/2) upper-packed %d x %d" % (m, n, qm, qn, qp_, qn, qn, qn),
+                  "route": "stock MatOp route (transform_ge + transform_sp per block, no pair fusion)"}
+    else:
+        cone, n = spec["cone"], spec["n"]
+        m = cone_rows(cone)
+        dense_elems = m * n
+        config = {"workload": args.workload, "cone": cone_text(cone), "A": "%d x %d dense column-major" % (m, n),
+                  "route": "fused DenseOp + ProductCone handed to the unmodified Solver"}
+    config["l2"] = "matrices (%.2f GB) are larger than L2; no explicit flush" % (dense_elems * esize / 1e9) if dense_elems * esize > 200e6 else \
+                   "matrices (%.3f GB) fit in the 126 MB L2: numbers are L2-resident, not HBM" % (dense_elems * esize / 1e9)
     steps, warmup = args.steps, max(args.warmup, 3)
-    config = {"workload": args.workload, "cone": ("%d x ConeSOC(%d)" % (nblk, bdim)) if bdim > 1 else "ConeRPos(%d)" % m, "A": "%d x %d dense column-major" % (m, n),
-              "l2": "A (%.2f GB) is larger than L2; no explicit flush" % (m * n * (4 if args.dtype == "f32" else 8) / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
             return
         ref_steps = min(steps, 20)
-        ref = cpu_reference_leg(nblk, bdim, n, ref_steps, min(warmup, 3), args.cpu_sample_blocks)
+        ref = cpu_reference_leg(spec, ref_steps, min(warmup, 3), args.cpu_sample_blocks)
         line = {"impl": "reference", "metric": "solver iterations/sec", "value": ref["value"], "unit": "iterations/s", "n_gpus": 0,
                 "steps": ref_steps, "warmup": min(warmup, 3), "ms_per_step": 1e3 / ref["value"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": ref,
@@ -209,12 +306,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: totsu_b200 has no CPU fallback")
     dt = np.float32 if args.dtype == "f32" else np.float64
-    esize = np.dtype(dt).itemsize
     torch.cuda.set_device(local_rank)
     capi.init(local_rank)
     L = capi.lib()
     capi.check(L.tb_set_pair_fusion(1 if args.pair_fusion else 0))
     if world > 1:
+        if is_qp or spec["cone"][0] == "psd":
+            raise SystemExit("%s is a single-GPU configuration (a PSD block / the QP front-end does not shard)" % args.workload)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         idbuf = (C.c_ubyte * capi.NCCL_ID_BYTES)()
@@ -229,24 +327,42 @@ def main():
         config["collectives"] = ("peer stores fused into the matvec epilogue (cudaIpc staging over NVLink)" if p2p.value
                                  else "ncclAllGather / ncclAllReduce")
         config["parallelism"] = "A row-sharded x%d on cone-block boundaries, vectors replicated" % world
-    from totsu_b200 import shard
-    blocks = [(capi.CONE_SOC, bdim)] * nblk if bdim > 1 else [(capi.CONE_RPOS, m)]
-    row_off, m_loc = shard.row_shards(blocks, world)[rank]
 
-    # ---- instance: A generated in HBM (shard), b = A x0 + s0, c = -A^T y0 through the backend itself
-    abuf = capi.Buf(dtype=dt, length=m_loc * n)
-    scale = dt(1.0 / math.sqrt(n))
-    capi.check(capi.fn("tb_fill_uniform", dt)(abuf.view(), m_loc, n, row_off, SEED, scale))
-    hop = C.c_int64()
-    capi.check(L.tb_denseop_create(capi.dtype_id(dt), abuf.view(), m_loc, n, row_off, m, C.byref(hop)))
-    x0, s0, y0 = instance_vectors(nblk, bdim, n, SEED)
-    b = s0.astype(dt); c = np.zeros(n, dtype=dt)
-    bx, by, bb, bc = capi.Buf(x0.astype(dt), mutable=False), capi.Buf(y0.astype(dt), mutable=False), capi.Buf(b), capi.Buf(c)
-    capi.check(capi.fn("tb_denseop_apply", dt)(hop.value, 0, 1.0, bx.view(), 1.0, bb.view()))
-    capi.check(capi.fn("tb_denseop_apply", dt)(hop.value, 1, -1.0, by.view(), 0.0, bc.view()))
-    for bf in (bx, by, bb, bc):
-        bf.release()
-    capi.check(L.tb_denseop_destroy(hop.value))
+    abuf = None
+    if is_qp:
+        qdata = qp_instance(qn, qm, qp_, dt)
+        m_loc = m
+        matrix_h2d = dense_elems * esize            # wrapped host arrays: uploaded on first use inside Solver::solve
+
+        def new_session():
+            return host.Session.qp(dt, qdata[0], qdata[1], qdata[2], qdata[3], qdata[4], qdata[5], 1e-12, p_is_sqrt=True, col_major=True)
+    else:
+        from totsu_b200 import shard
+        if cone[0] == "soc":
+            blocks = [(capi.CONE_SOC, cone[2])] * cone[1]
+        elif cone[0] == "rpos":
+            blocks = [(capi.CONE_RPOS, m)]
+        else:
+            blocks = [(capi.CONE_PSD, m)]
+        row_off, m_loc = shard.row_shards(blocks, world)[rank]
+        matrix_h2d = 0                              # A is generated in HBM
+        # ---- instance: A generated in HBM (shard), b = A x0 + s0, c = -A^T y0 through the backend itself
+        abuf = capi.Buf(dtype=dt, length=m_loc * n)
+        scale = dt(1.0 / math.sqrt(n))
+        capi.check(capi.fn("tb_fill_uniform", dt)(abuf.view(), m_loc, n, row_off, SEED, scale))
+        hop = C.c_int64()
+        capi.check(L.tb_denseop_create(capi.dtype_id(dt), abuf.view(), m_loc, n, row_off, m, C.byref(hop)))
+        x0, s0, y0 = instance_vectors(cone, n, SEED)
+        b = s0.astype(dt); c = np.zeros(n, dtype=dt)
+        bx, by, bb, bc = capi.Buf(x0.astype(dt), mutable=False), capi.Buf(y0.astype(dt), mutable=False), capi.Buf(b), capi.Buf(c)
+        capi.check(capi.fn("tb_denseop_apply", dt)(hop.value, 0, 1.0, bx.view(), 1.0, bb.view()))
+        capi.check(capi.fn("tb_denseop_apply", dt)(hop.value, 1, -1.0, by.view(), 0.0, bc.view()))
+        for bf in (bx, by, bb, bc):
+            bf.release()
+        capi.check(L.tb_denseop_destroy(hop.value))
+
+        def new_session():
+            return host.Session.dense(dt, abuf.view(), m_loc, n, c, b, blocks, fused_op=True, fused_cone=True, row_offset=row_off, m_total=m)
 
     stream = torch.cuda.ExternalStream(capi.stream_ptr(), device=torch.device("cuda", local_rank))
 
@@ -256,18 +372,14 @@ def main():
         if world > 1:
             torch.distributed.barrier()
 
-    def new_session():
-        s = host.Session.dense(dt, abuf.view(), m_loc, n, c, b, blocks, fused_op=True, fused_cone=True, row_offset=row_off, m_total=m)
-        return s
-
     # ---- device-resident timing: K iterations between two events on the library's stream
     s = new_session()
-    assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+    assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=not is_qp) == "None"
     if os.environ.get("BENCH_DEBUG"):
         for _ in range(min(warmup, 5)):
             s.step(1)
             print("dbg iter %d tau %.4e res %.4e %.4e %.4e" % (s.last.i, s.last.val_tau, s.last.c0, s.last.c1, s.last.c2), file=sys.stderr)
-        print("dbg b[:4]", b[:4], "c[:4]", c[:4], "norms", s.norms(), file=sys.stderr)
+        print("dbg norms", s.norms(), file=sys.stderr)
         warmup = max(0, warmup - 5)
     s.step(warmup)
     barrier()
@@ -293,12 +405,12 @@ def main():
     capi.check(L.tb_prof_enable(0))
     s.close()
 
-    # ---- end to end: one whole Solver::solve through the public API with host buffers (work, c, b on the host;
-    # scalars cross the boundary every iteration; the solution is read back)
+    # ---- end to end: one whole Solver::solve through the public API with host buffers (work, c, b - and for the QP
+    # front-end the matrices - in host memory; scalars cross the boundary every iteration; the solution is read back)
     barrier()
     s = new_session()
     t0 = time.perf_counter()
-    st = s.begin(max_iter=steps, eps_acc=0.0, eps_inf=0.0, device_precond=True)
+    st = s.begin(max_iter=steps, eps_acc=0.0, eps_inf=0.0, device_precond=not is_qp)
     assert st == "None"
     t1 = time.perf_counter()
     st, _ = s.run()
@@ -312,7 +424,7 @@ def main():
         print("dbg e2e: begin %.4f s, run %.4f s, end+readback %.4f s" % (t1 - t0, t2 - t1, t0 + t_e2e - t2), file=sys.stderr)
     s.close()
     worklen = 4 * (n + 2 * m + 1) + 2 * (n + m + 1)
-    h2d = worklen * esize / steps + 3 * esize          # work upload amortised + tau/kappa/unit scalars per iteration
+    h2d = (worklen * esize + matrix_h2d) / steps + 3 * esize          # work (+ wrapped matrices) upload amortised + tau/kappa/unit scalars per iteration
     d2h = (n + m) * esize / steps + 6 * esize          # solution readback amortised + tau, kappa, g_x, g_y, |p|, |d|
 
     # ---- max over ranks
@@ -334,26 +446,29 @@ def main():
         vals = [v["dram_bytes_per_launch"] for k, v in tj.items() if k.startswith(args.workload + "|") and want in k]
         if vals:
             traffic = sum(vals) / len(vals)
+    local_elems = dense_elems if is_qp else m_loc * n
     if nl.value:
-        # ALGORITHMIC bytes per launch: one read of this rank's A per op / trans_op served.  With the
-        # lazy pairing a launch serves an op AND a trans_op from ONE read of A, so the algorithmic figure is twice the
-        # bytes actually streamed and `frac` may exceed 1; `streamed_*` is the un-doubled DRAM-side figure.
+        # ALGORITHMIC bytes per launch: one read of this rank's dense block per op / trans_op served.  With
+        # the lazy pairing a launch serves an op AND a trans_op from ONE read of A, so the algorithmic figure is twice the
+        # bytes actually streamed and `frac` may exceed 1; `streamed_*` is the un-doubled DRAM-side figure.  (QP: the
+        # launches timed are the transform_ge ones on G and A_eq; the packed P^(1/2) goes through spmv_kernel.)
         avg_ms = kms.value / nl.value
-        alg_per_launch = 6.0 * prof_iters * m_loc * n * esize / nl.value
+        ge_elems = (qm * qn + qp_ * qn) if is_qp else m_loc * n
+        alg_per_launch = 6.0 * prof_iters * ge_elems * esize / nl.value
         ach = alg_per_launch / (avg_ms * 1e-3) / 1e9
         streamed = (kbytes.value / nl.value) / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "stream_kernel (TMA bulk-copy matvec)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture)" if traffic else None, "peak_source": peak_src, "launches_timed": int(nl.value), "avg_launch_ms": avg_ms,
-                "algorithmic_bytes_per_launch": alg_per_launch, "matvecs_per_launch": 6.0 * prof_iters / nl.value,
+                "algorithmic_bytes_per_launch": alg_per_launch, "matvecs_per_launch": 6.0 * prof_iters * (2 if is_qp else 1) / nl.value,
                 "streamed_bytes_per_launch": kbytes.value / nl.value, "streamed_gbs": streamed, "streamed_frac": streamed / peak,
                 "note": ("op/trans_op pairs share one read of A (lazy pairing behind tb_denseop_apply): achieved/frac use the un-fused "
                          "algorithmic bytes and can exceed 1; streamed_frac is bytes actually read / peak") if pairs_per_iter else None}
-    abytes_iter = 6.0 * m * n * esize
+    abytes_iter = 6.0 * dense_elems * esize
     line = {"metric": "solver iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "Solver::solve (begin + %d iterations + end) through the host layer, work/c/b in host memory" % steps,
+                    "what": "Solver::solve (begin + %d iterations + end) through the host layer, work/c/b%s in host memory" % (steps, " and the matrices" if is_qp else ""),
                     "breakdown_s": {"begin": t1 - t0, "iterate": t2 - t1, "end_and_readback": t0 + t_e2e_local - t2}},
             "gpu_launches": int(launches), "roofline": roof,
             "hbm_frac_whole_iteration": abytes_iter * value / (world * peak * 1e9),
@@ -361,9 +476,10 @@ def main():
             "clocks": clk, "last_residuals": [last.c0, last.c1, last.c2], "status_e2e": st}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_leg(nblk, bdim, n, 6, 2, args.cpu_sample_blocks)
+            line["cpu_baseline"] = cpu_reference_leg(spec, 6, 2, args.cpu_sample_blocks)
         print(json.dumps(line))
-    abuf.release()
+    if abuf is not None:
+        abuf.release()
     if world > 1:
         capi.check(L.tb_dist_finalize())
         torch.distributed.destroy_process_group()

@@ -140,6 +140,10 @@ int tb_set_psd_path(int mode);
  * and the tensor-pipe measurement of config C4.  tb_set_psd_path: 0 = sign iteration (tcgen05 for f32), 1 = Jacobi,
  * 2 = sign iteration on the FP32/FP64 pipes, 3 = tcgen05 without split-K. */
 int tb_symm_gemm_f32(size_t k, float alpha, tb_view a, tb_view b, float beta, tb_view d, float gamma, tb_view c, int engine, int splitk);
+/* Diagnostics: `reps` back-to-back tensor-core GEMMs c = a*b; the last one records %globaltimer stamps (ns) of CTA 0
+ * at its phases into stamps_ns[0..8]: entered, prologue done, dependency resolved, first chunk staged, producers
+ * done, accumulator complete, partials pushed, cluster barrier passed, results stored. */
+int tb_symm_gemm_trace_f32(size_t k, tb_view a, tb_view b, tb_view c, int splitk, int reps, uint64_t* stamps_ns);
 int tb_proj_psd_f32(tb_view x, float eps_zero, tb_view work);
 int tb_proj_psd_f64(tb_view x, double eps_zero, tb_view work);
 

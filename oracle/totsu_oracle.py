@@ -113,6 +113,14 @@ class F64LAPACK:
     @staticmethod
     def transform_sp(n, alpha, mat, x, beta, y) -> None:     # :149-163 (dspmv Upper, packed by columns)
         assert mat.size == n * (n + 1) // 2 and x.size == n and y.size == n
+        if n == 0:
+            return
+        if mat.dtype == np.float64 and x.dtype == np.float64 and y.dtype == np.float64:
+            # the same BLAS routine the reference calls (cblas::dspmv, ColumnMajor, Upper): packed index c*(c+1)/2 + r
+            from scipy.linalg.blas import dspmv
+            r = dspmv(n, alpha, mat, np.ascontiguousarray(x), beta=beta, y=np.array(y, dtype=np.float64), lower=0, overwrite_y=1)
+            y[...] = r
+            return
         full = np.zeros((n, n), dtype=mat.dtype)
         # packed index c*(c+1)/2 + r (r <= c): iterate columns, rows within column
         full.T[np.tril_indices(n)] = mat           # full.T lower (c, r<=c) row-major == packed order
@@ -954,12 +962,14 @@ class _QPOpB:                                                # qp.rs:174-258
 
 
 class ProbQP:                                                # qp.rs:300-437
-    def __init__(self, sym_p, vec_q, mat_g, vec_h, mat_a, vec_b, eps_zero):
+    def __init__(self, sym_p, vec_q, mat_g, vec_h, mat_a, vec_b, eps_zero, p_is_sqrt=False):
+        """p_is_sqrt: `sym_p` already holds P^(1/2) (bench shortcut for config C2's diagonal P, where the n = 8192
+        eigendecomposition of qp.rs:386 `set_sqrt` would take minutes and is not part of the timed iteration)."""
         n, m, p = vec_q.size()[0], vec_h.size()[0], vec_b.size()[0]
         assert sym_p.is_sympack() and sym_p.size() == (n, n)
         assert mat_g.size() == (m, n) and mat_a.size() == (p, n)
         self.vec_q, self.mat_g, self.vec_h, self.mat_a, self.vec_b = vec_q, mat_g, vec_h, mat_a, vec_b
-        self.sym_p_sqrt = sym_p.sqrt(eps_zero)
+        self.sym_p_sqrt = sym_p if p_is_sqrt else sym_p.sqrt(eps_zero)
 
     def problem(self):
         n, m, p = self.vec_q.size()[0], self.vec_h.size()[0], self.vec_b.size()[0]

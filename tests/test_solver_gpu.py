@@ -130,6 +130,7 @@ SYN = {
     "qp_like": (lambda: ([(ROTSOC, 66), (RPOS, 64), (ZERO, 10)], 65)),
     "sdp_like": (lambda: ([(PSD, 36), (RPOS, 10), (ZERO, 3)], 20)),
     "stream": (lambda: ([(SOC, 64)] * 32 + [(RPOS, 512)], 1024)),      # 2560 x 1024: large enough for the TMA kernel
+    "sdp_tc": (lambda: ([(PSD, 2080)], 40)),                           # k = 64: the f32 projection runs on the tcgen05 GEMMs
 }
 
 
@@ -143,7 +144,7 @@ def test_iterates_match_oracle(name, dt):
     snaps, trace = H.oracle_iterates(a, b, c, blocks, ks)
     # stated tolerances: relative l_inf of x_hat / y_hat vs the f64 oracle
     tol = {np.float64: {1: 1e-12, 10: 1e-11, 100: 1e-9}, np.float32: {1: 5e-6, 10: 5e-5, 100: 1e-4}}[dt]
-    if name == "sdp_like":
+    if name in ("sdp_like", "sdp_tc"):
         tol = {k: v * (100 if dt == np.float32 else 1e4) for k, v in tol.items()}      # eigensolver conditioning
     abuf, av = H.device_matrix(a)
     results = {}
@@ -161,7 +162,7 @@ def test_iterates_match_oracle(name, dt):
             it = s.last
             ref = trace[k - 1]
             rt = 5e-3 if dt == np.float32 else 1e-8
-            if name == "sdp_like":
+            if name in ("sdp_like", "sdp_tc"):
                 rt *= 20
             for got, want in zip((it.c0, it.c1, it.c2), ref[1:]):
                 if not np.isfinite(want):          # criteria_inf branch: inf when m_cx / m_by <= eps_zero (solver.rs:640-653)
@@ -286,3 +287,52 @@ def test_pair_fusion_hazards(dt):
     finally:
         capi.check(L.tb_denseop_destroy(h.value))
         abuf.release()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("presqrt", [False, True])
+def test_front_end_qp_iterates_match_oracle(dt, presqrt):
+    """Config C2's shape in small: the ProbQP front-end (qp.rs:300-437: rows [0; q^T,-1; -P^(1/2); G; A], cone
+    RotSOC(n+2) x RPos(m) x Zero(p)) through the stock MatOp route - transform_sp on the packed P^(1/2), transform_ge
+    on G and A - against the oracle's ProbQP iterates after K = 1, 10, 100.  presqrt=False: P^(1/2) comes from the
+    device map_eig closure path (MatBuild::set_sqrt, qp.rs:386); True: the caller supplies it (what bench.py's C2 does)."""
+    import totsu_oracle as O
+    n, m, p = 48, 40, 6
+    rng = np.random.default_rng(42)
+    g0 = rng.standard_normal((n, n))
+    pm = (g0 @ g0.T / n + 0.1 * np.eye(n)).astype(dt).astype(np.float64)
+    w, v = np.linalg.eigh(pm)
+    psq = ((v * np.sqrt(w)) @ v.T)
+    pack = lambda a: np.array([a[r, c] for c in range(n) for r in range(c + 1)])
+    sym = pack(psq if presqrt else pm).astype(dt)
+    gm = (rng.standard_normal((m, n)) / math.sqrt(n)).astype(dt)
+    am = (rng.standard_normal((p, n)) / math.sqrt(n)).astype(dt)
+    x0 = rng.standard_normal(n)
+    h = (gm.astype(np.float64) @ x0 + np.abs(rng.standard_normal(m)) + 0.1).astype(dt)
+    b = (am.astype(np.float64) @ x0).astype(dt)
+    q = rng.standard_normal(n).astype(dt)
+    f8 = lambda a: np.asarray(a, dtype=np.float64)
+    prob = O.ProbQP(O.MatBuild(O.MatType.SymPack(n), f8(sym)), O.MatBuild(O.MatType.General(n, 1), f8(q)),
+                    O.MatBuild(O.MatType.General(m, n), f8(gm).reshape(-1, order="F")), O.MatBuild(O.MatType.General(m, 1), f8(h)),
+                    O.MatBuild(O.MatType.General(p, n), f8(am).reshape(-1, order="F")), O.MatBuild(O.MatType.General(p, 1), f8(b)), 1e-12, p_is_sqrt=presqrt)
+    ks = [1, 10, 100]
+    so = O.Solver()
+    so.par.max_iter = max(ks) + 2; so.par.eps_acc = 0.0; so.par.eps_inf = 0.0
+    so.snapshots = {k: None for k in ks}
+    so.trace = []
+    try:
+        so.solve(prob.problem())
+    except O.SolverError:
+        pass
+    s = host.Session.qp(dt, sym, q, gm, h, am, b, 1e-12, p_is_sqrt=presqrt)
+    assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0) == "None"
+    tol = {np.float64: {1: 1e-12, 10: 1e-11, 100: 1e-9}, np.float32: {1: 5e-6, 10: 5e-5, 100: 1e-4}}[dt]
+    if not presqrt:      # the two square roots (LAPACK dsyevr vs device Jacobi) differ at the eigensolver's accuracy
+        tol = {k: max(v * 20, 1e-10) for k, v in tol.items()}
+    done = 0
+    for k in ks:
+        s.step(k - done); done = k
+        xh, yh = s.xy()
+        ex, ey = H.rel_linf(xh, so.snapshots[k][0]), H.rel_linf(yh, so.snapshots[k][1])
+        assert ex <= tol[k] and ey <= tol[k], (dt, presqrt, k, ex, ey)
+    s.close()

@@ -61,6 +61,7 @@ def _signatures():
         "tb_upload": (i, [View, vp]), "tb_download": (i, [View, vp]),
         "tb_map_eig_worklen": (sz, [sz]),
         "tb_symm_gemm_f32": (i, [sz, C.c_float, View, View, C.c_float, View, C.c_float, View, i, i]),
+        "tb_symm_gemm_trace_f32": (i, [sz, View, View, View, i, i, C.POINTER(u64)]),
         "tb_denseop_create": (i, [i, View, sz, sz, sz, sz, C.POINTER(H)]), "tb_denseop_destroy": (i, [H]),
         "tb_cone_create": (i, [C.POINTER(ConeBlock), sz, C.POINTER(H)]), "tb_cone_destroy": (i, [H]),
         "tb_dist_unique_id": (i, [vp]), "tb_dist_init": (i, [i, i, vp]), "tb_dist_finalize": (i, []),

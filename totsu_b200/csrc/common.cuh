@@ -262,7 +262,8 @@ void dist_check_fault();      // throws if a peer-exchange wait timed out
 template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len);
 // tcgen05 3xTF32 symmetric GEMM (psd_tc.cu): C = alpha*A*B + beta*D + gamma*I, all symmetric k x k column-major f32
 bool symm_gemm_tc_usable(const float* A, const float* B, const float* D, const float* C, size_t k);
-void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk);
+void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk,
+                  unsigned long long* trace = nullptr);   // trace: 16 device u64 phase stamps of CTA 0 (diagnostics)
 
 }  // namespace tb
 

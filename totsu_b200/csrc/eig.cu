@@ -491,6 +491,22 @@ int tb_symm_gemm_f32(size_t k, float alpha, tb_view a, tb_view b, float beta, tb
         symm_gemm<float>(pa, pb, pd, pc, k, alpha, beta, gamma, nullptr, engine, splitk);
     });
 }
+int tb_symm_gemm_trace_f32(size_t k, tb_view a, tb_view b, tb_view cv, int splitk, int reps, uint64_t* stamps_ns) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(a.len == k * k && b.len == k * k && cv.len == k * k && reps >= 1, "symm_gemm_trace: every matrix is k x k");
+        const float* pa = rptr<float>(a);
+        const float* pb = rptr<float>(b);
+        float* pc = wptr<float>(cv, true);
+        unsigned long long* dev = nullptr;
+        TB_CUDA(cudaMalloc(&dev, 16 * sizeof(unsigned long long)));
+        TB_CUDA(cudaMemsetAsync(dev, 0, 16 * sizeof(unsigned long long), ctx().stream));
+        for (int r = 0; r < reps; ++r) symm_gemm_tc(pa, pb, nullptr, pc, k, 1.f, 0.f, 0.f, splitk, r == reps - 1 ? dev : nullptr);
+        TB_CUDA(cudaMemcpyAsync(stamps_ns, dev, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx().stream));
+        TB_CUDA(cudaStreamSynchronize(ctx().stream));
+        TB_CUDA(cudaFree(dev));
+    });
+}
 int tb_proj_psd_f32(tb_view x, float ez, tb_view w) { return api([&] { api_proj_psd<float>(x, ez, w); }); }
 int tb_proj_psd_f64(tb_view x, double ez, tb_view w) { return api([&] { api_proj_psd<double>(x, ez, w); }); }
 }

@@ -10,8 +10,9 @@
 //     (A symmetric) is column i - so a tile row is a contiguous run of K in global memory;
 //   * 8 producer warps read 128-byte row segments (L2-resident: the matrices are <= a few MB), split hi/lo in
 //     registers and store both into the canonical no-swizzle K-major core-matrix layout (8 rows x 16 B contiguous,
-//     LBO = 128 B along K, SBO = 1024 B along M/N), 3-stage mbarrier ring; one elected lane of warp 8 issues the MMAs
-//     and releases stages with tcgen05.commit;
+//     LBO = 144 B along K - a 16-byte skew that makes coalesced global reads and conflict-free shared stores
+//     compatible - SBO = 1152 B along M/N), mbarrier ring + one chunk prefetched in registers; one elected lane of
+//     warp 8 issues the MMAs and releases stages with tcgen05.commit;
 //   * split-K across a thread-block cluster (1,1,S), S <= 8: each CTA owns K/S of the reduction; from TMEM it PUSHES
 //     (st.shared::cluster) the rows [z'*128/S, (z'+1)*128/S) of its partial tile into the inbox of CTA z', and after one
 //     cluster barrier every CTA sums the S partials of its own rows from local shared memory in rank order (fixed
@@ -34,10 +35,13 @@ namespace tc {
 constexpr int TM = 128, TN = 128, KC = 32;
 constexpr int PRODUCER_WARPS = 8;
 constexpr int THREADS = (PRODUCER_WARPS + 1) * 32;
-constexpr int TILE_BYTES = TM * KC * 4;           // one operand half (hi or lo) of one stage: 16 KB
+// Core matrices (8 rows x 16 B = 128 B) are laid out 144 B apart along K: the 16-byte skew puts the eight 16-byte
+// K-chunks of one row into eight different bank groups, so a quarter-warp can read one row's contiguous 128 B from
+// global memory (fully coalesced: one L1 tag per quarter-warp) AND store them to shared memory conflict-free.
+constexpr int LBO = 144;                          // next core matrix along K
+constexpr int SBO = (KC / 4) * LBO;               // next 8-row group along M/N: 1152 B
+constexpr int TILE_BYTES = (TM / 8) * SBO;        // one operand half (hi or lo) of one stage: 18 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;       // A_hi | A_lo | B_hi | B_lo
-constexpr int LBO = 128;                          // next core matrix along K
-constexpr int SBO = (KC / 4) * 128;               // next 8-row group along M/N: 1024 B
 constexpr int PAD = TM + 1;                       // padded leading dimension of the staging tiles
 constexpr int TMEM_COLS = 128;
 static_assert(TM == TN, "the staging tiles assume square tiles");
@@ -150,6 +154,14 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// phase stamps of CTA 0 (diagnostics: tb_symm_gemm_trace); slot i of `trace` is written by one thread
+#define TC_STAMP(i) do { if (trace != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && (tid == 0)) trace[i] = gtimer(); } while (0)
+
 template <int SPLITK> struct Cfg {
     static constexpr int STAGES = SPLITK > 1 ? 2 : 3;             // + one chunk in flight in registers
     static constexpr int ROWS = TM / SPLITK;                      // tile rows this CTA finishes after the split-K exchange
@@ -163,7 +175,8 @@ template <int SPLITK> struct Cfg {
 // grid = (upper tile pairs, 1, SPLITK), cluster (1, 1, SPLITK).
 template <int SPLITK>
 __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ D,
-                                                                  float* __restrict__ C, int k, float alpha, float beta, float gamma, uint64_t dfields) {
+                                                                  float* __restrict__ C, int k, float alpha, float beta, float gamma, uint64_t dfields,
+                                                                  unsigned long long* __restrict__ trace) {
     using G = Cfg<SPLITK>;
     constexpr int STAGES = G::STAGES, ROWS = G::ROWS;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accf + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TC_STAMP(0);                           // kernel entered
     // decode the upper tile pair (bi <= bj) from blockIdx.x: row bi holds nt - bi tiles
     const int nt = (k + TM - 1) / TM;
     int bi = 0, rem = blockIdx.x;
@@ -195,19 +209,21 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    TC_STAMP(1);                           // prologue done (barriers, TMEM)
     if (SPLITK > 1) cluster_arrive();      // "I have started": matched by cluster_wait() before the first remote store
     pdl_wait();                            // the producing kernel's stores are visible from here on
     pdl_launch_dependents();               // the next kernel may run its prologue while this one works
+    TC_STAMP(2);                           // dependency resolved
 
     if (warp < PRODUCER_WARPS) {
         // ---- producers: global (L2) -> registers -> hi/lo split -> canonical K-major core matrices in smem
-        const int r8 = lane & 7, cq = lane >> 3;
+        // lane -> (row within a group of 4, 16-byte K chunk): a quarter-warp covers one row's 128 contiguous bytes
+        const int r4 = lane >> 3, ck = lane & 7;
         auto load = [&](int chunk, float4* v) {
-            const int l0 = chunk * KC;
+            const int kk = chunk * KC + ck * 4;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int u = warp + PRODUCER_WARPS * q;          // (row group, K half) unit: 16 x 2 per operand tile
-                const int row = (u >> 1) * 8 + r8, kk = l0 + ((u & 1) * 4 + cq) * 4;
+                const int row = q * 32 + warp * 4 + r4;
                 const int gi = i0 + row, gj = j0 + row;
                 v[q] = (gi < k && kk < k) ? *reinterpret_cast<const float4*>(A + (size_t)gi * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[4 + q] = (gj < k && kk < k) ? *reinterpret_cast<const float4*>(B + (size_t)gj * k + kk) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -223,8 +239,8 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
             uint8_t* st = smem + s * STAGE_BYTES;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int u = warp + PRODUCER_WARPS * q;
-                const int off = (u >> 1) * SBO + ((u & 1) * 4 + cq) * LBO + r8 * 16;
+                const int row = q * 32 + warp * 4 + r4;
+                const int off = (row >> 3) * SBO + ck * LBO + (row & 7) * 16;
                 float4 hi, lo;
                 split_tf32(cur[q], hi, lo);
                 *reinterpret_cast<float4*>(st + off) = hi;
@@ -235,6 +251,7 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
             }
             fence_async_shared();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
             mbar_arrive(&full[s]);
+            if (it == 0) TC_STAMP(3);      // first chunk loaded, split and stored
 #pragma unroll
             for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
         }
@@ -269,7 +286,9 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     if (warp < PRODUCER_WARPS) {
         const int quad = warp & 3, chalf = warp >> 2;
         const int row = quad * 32 + lane;
+        TC_STAMP(4);                       // producers done
         if (nmy > 0) { mbar_wait(accf, 0u); tc_fence_after(); }
+        TC_STAMP(5);                       // accumulator complete
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
             const int cbase = chalf * 64 + cc * 32;
@@ -303,8 +322,10 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
     }
     tc_fence_before();
     if (SPLITK > 1) {
+        TC_STAMP(6);                        // partial sums pushed
         cluster_arrive();
         cluster_wait();                     // all partial sums have landed; nothing remote is touched after this point
+        TC_STAMP(7);
         if (warp < PRODUCER_WARPS) {
             for (int idx = tid; idx < TN * ROWS; idx += PRODUCER_WARPS * 32) {
                 const int i = idx % ROWS, j = idx / ROWS;
@@ -321,8 +342,10 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
                 Rt[i * PAD + j] = val;
             }
         }
+        TC_STAMP(9);                        // own rows reduced and stored (warp 0)
     }
     __syncthreads();
+    TC_STAMP(10);
     if (warp < PRODUCER_WARPS) {
         // mirror: rows of the finished block become columns of C below the diagonal (coalesced along j)
         for (int i = warp; i < ROWS; i += PRODUCER_WARPS) {
@@ -334,6 +357,7 @@ __global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* _
         }
     }
     __syncthreads();
+    TC_STAMP(8);                            // results stored
     tc_fence_after();
     if (warp == PRODUCER_WARPS) tmem_dealloc(tmem_base);
 }
@@ -343,7 +367,8 @@ static bool env_flag(const char* name, bool dflt) {
     return e ? e[0] != '0' : dflt;
 }
 
-template <int SPLITK> static void launch(const float* A, const float* B, const float* D, float* C, int k, float alpha, float beta, float gamma) {
+template <int SPLITK> static void launch(const float* A, const float* B, const float* D, float* C, int k, float alpha, float beta, float gamma,
+                                          unsigned long long* trace) {
     static bool configured = false;
     auto kern = symm_gemm_tc_kernel<SPLITK>;
     if (!configured) {
@@ -377,7 +402,7 @@ template <int SPLITK> static void launch(const float* A, const float* B, const f
     // TB_TC_DESC_SWAP=1 (debug) exchanges the leading/stride byte offsets of the operand descriptors
     static const bool swap = env_flag("TB_TC_DESC_SWAP", false);
     const uint64_t dfields = swap ? smem_desc_fields(SBO, LBO) : smem_desc_fields(LBO, SBO);
-    TB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, B, D, C, k, alpha, beta, gamma, dfields));
+    TB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, B, D, C, k, alpha, beta, gamma, dfields, trace));
     count_launch();
 }
 
@@ -389,7 +414,8 @@ bool symm_gemm_tc_usable(const float* A, const float* B, const float* D, const f
 }
 
 // splitk: 0 = choose, else 1 / 2 / 4
-void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk) {
+void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk,
+                  unsigned long long* trace) {
     TB_REQUIRE(symm_gemm_tc_usable(A, B, D, C, k), "tensor-core symmetric GEMM needs k % 4 == 0 and 16-byte aligned matrices");
     TB_REQUIRE(C != A && C != B && C != D, "symm_gemm: the output must not alias an input");
     if (splitk == 0) {
@@ -400,10 +426,10 @@ void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size
         while (splitk < cap && pairs * (size_t)splitk * 2 <= (size_t)ctx().sm_count && nk / (size_t)(splitk * 2) >= 2) splitk *= 2;
     }
     switch (splitk) {
-        case 1: tc::launch<1>(A, B, D, C, (int)k, alpha, beta, gamma); break;
-        case 2: tc::launch<2>(A, B, D, C, (int)k, alpha, beta, gamma); break;
-        case 4: tc::launch<4>(A, B, D, C, (int)k, alpha, beta, gamma); break;
-        case 8: tc::launch<8>(A, B, D, C, (int)k, alpha, beta, gamma); break;
+        case 1: tc::launch<1>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
+        case 2: tc::launch<2>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
+        case 4: tc::launch<4>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
+        case 8: tc::launch<8>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
         default: fail(TB_ERR_ARG, "symm_gemm_tc: splitk must be 0, 1, 2, 4 or 8");
     }
 }

@@ -41,7 +41,7 @@ def hlib():
         L.tbh_session_lp.restype = vp
         L.tbh_session_lp.argtypes = [i, sz, sz, sz, vp, vp, vp, vp, vp]
         L.tbh_session_qp.restype = vp
-        L.tbh_session_qp.argtypes = [i, sz, sz, sz, vp, vp, vp, vp, vp, vp, d]
+        L.tbh_session_qp.argtypes = [i, sz, sz, sz, vp, vp, vp, vp, vp, vp, d, i]
         L.tbh_session_qcqp.restype = vp
         L.tbh_session_qcqp.argtypes = [i, sz, sz, sz, vp, vp, vp, vp, vp, d]
         L.tbh_session_socp.restype = vp
@@ -107,15 +107,21 @@ class Session:
         return Session(hd, dt, (c, g, h, a, b))
 
     @staticmethod
-    def qp(dtype, sym_p_packed, vec_q, mat_g, vec_h, mat_a, vec_b, eps_zero):
+    def qp(dtype, sym_p_packed, vec_q, mat_g, vec_h, mat_a, vec_b, eps_zero, p_is_sqrt=False, col_major=False):
+        """p_is_sqrt: `sym_p_packed` already holds P^(1/2) (qp.rs:386 set_sqrt skipped); col_major: mat_g / mat_a are
+        given as flat column-major arrays (no transposing copy of a large G)."""
         dt = np.dtype(dtype)
         q = _arr(vec_q, dt); n = q.size
         h = _arr(vec_h, dt); m = h.size
         b = _arr(vec_b, dt); p = b.size
         sp = _arr(sym_p_packed, dt)
-        g = _arr(np.asarray(mat_g, dtype=dt).reshape(m, n), dt, "F")
-        a = _arr(np.asarray(mat_a, dtype=dt).reshape(p, n), dt, "F")
-        hd = hlib().tbh_session_qp(dtype_id(dt), n, m, p, _p(sp), _p(q), _p(g), _p(h), _p(a), _p(b), eps_zero)
+        if col_major:
+            g, a = _arr(mat_g, dt), _arr(mat_a, dt)
+            assert g.size == m * n and a.size == p * n
+        else:
+            g = _arr(np.asarray(mat_g, dtype=dt).reshape(m, n), dt, "F")
+            a = _arr(np.asarray(mat_a, dtype=dt).reshape(p, n), dt, "F")
+        hd = hlib().tbh_session_qp(dtype_id(dt), n, m, p, _p(sp), _p(q), _p(g), _p(h), _p(a), _p(b), eps_zero, 1 if p_is_sqrt else 0)
         return Session(hd, dt, (sp, q, g, h, a, b))
 
     @staticmethod

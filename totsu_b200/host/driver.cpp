@@ -151,9 +151,10 @@ SessionBase* make_lp(size_t n, size_t m, size_t p, const void* c, const void* g,
     return s;
 }
 template <typename F>
-SessionBase* make_qp(size_t n, size_t m, size_t p, const void* sym_p, const void* q, const void* g, const void* h, const void* a, const void* b, double eps_zero) {
+SessionBase* make_qp(size_t n, size_t m, size_t p, const void* sym_p, const void* q, const void* g, const void* h, const void* a, const void* b, double eps_zero,
+                     int p_is_sqrt) {
     auto* pr = new ProbQP<F>(mb_sym<F>(n, sym_p), mb_general<F>(n, 1, q), mb_general<F>(m, n, g), mb_general<F>(m, 1, h),
-                             mb_general<F>(p, n, a), mb_general<F>(p, 1, b), (F)eps_zero);
+                             mb_general<F>(p, n, a), mb_general<F>(p, 1, b), (F)eps_zero, p_is_sqrt != 0);
     auto* s = new Session<F>();
     s->prob.reset(pr);
     pr->problem();
@@ -276,8 +277,9 @@ const char* tbh_last_error(void) { return g_err.c_str(); }
 void* tbh_session_lp(int dtype, size_t n, size_t m, size_t p, const void* c, const void* g, const void* h, const void* a, const void* b) {
     return guarded_new([&] { return (void*)DISPATCH(dtype, make_lp, n, m, p, c, g, h, a, b); });
 }
-void* tbh_session_qp(int dtype, size_t n, size_t m, size_t p, const void* sym_p, const void* q, const void* g, const void* h, const void* a, const void* b, double eps_zero) {
-    return guarded_new([&] { return (void*)DISPATCH(dtype, make_qp, n, m, p, sym_p, q, g, h, a, b, eps_zero); });
+void* tbh_session_qp(int dtype, size_t n, size_t m, size_t p, const void* sym_p, const void* q, const void* g, const void* h, const void* a, const void* b, double eps_zero,
+                     int p_is_sqrt) {
+    return guarded_new([&] { return (void*)DISPATCH(dtype, make_qp, n, m, p, sym_p, q, g, h, a, b, eps_zero, p_is_sqrt); });
 }
 void* tbh_session_qcqp(int dtype, size_t n, size_t m1, size_t p, const void* syms_p, const void* vecs_q, const void* scls_r, const void* a, const void* b, double eps_zero) {
     return guarded_new([&] { return (void*)DISPATCH(dtype, make_qcqp, n, m1, p, syms_p, vecs_q, scls_r, a, b, eps_zero); });

@@ -287,10 +287,11 @@ template <typename F> struct QPOpB : Operator<F> {               // qp.rs:174-25
 
 template <typename F> struct ProbQP : Problem<F> {               // qp.rs:300-437
     MatBuild<F> vec_q, mat_g, vec_h, mat_a, vec_b, sym_p_sqrt;
-    ProbQP(MatBuild<F> sym_p, MatBuild<F> q, MatBuild<F> g, MatBuild<F> h, MatBuild<F> a, MatBuild<F> b, F eps_zero)
+    // p_is_sqrt: sym_p already holds P^(1/2) (bench shortcut for config C2's diagonal P; qp.rs:386 is skipped)
+    ProbQP(MatBuild<F> sym_p, MatBuild<F> q, MatBuild<F> g, MatBuild<F> h, MatBuild<F> a, MatBuild<F> b, F eps_zero, bool p_is_sqrt = false)
         : vec_q(std::move(q)), mat_g(std::move(g)), vec_h(std::move(h)), mat_a(std::move(a)), vec_b(std::move(b)), sym_p_sqrt(std::move(sym_p)) {
         if (!sym_p_sqrt.is_sympack()) throw BackendError("ProbQP: sym_p must be SymPack");
-        sym_p_sqrt.set_sqrt(eps_zero);                           // qp.rs:386
+        if (!p_is_sqrt) sym_p_sqrt.set_sqrt(eps_zero);           // qp.rs:386
     }
     void problem() {
         const size_t n = vec_q.size().first, m = vec_h.size().first, p = vec_b.size().first;
