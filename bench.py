@@ -155,6 +155,26 @@ class Clocks:
         return out
 
 
+def qp_stacked(qn, qm, qp_, dt, qdata=None):
+    """ProbQP's composite operator written out as one dense matrix (qp.rs:98-140, rows [0; q^T,-1; -P^(1/2); G; A_eq],
+    columns (x, t)) with b = [1; 0; 0_n; h; b_eq] (qp.rs:196-215) and c = [0_n; 1] (qp.rs:20-45); zero rows are appended
+    to the ConeZero block so the row count is a multiple of 4 (16-byte aligned columns for the streaming kernel).
+    Returns (A column-major 2-D, b, c, n_pad_rows)."""
+    psqrt, q, g, h, a_eq, b_eq = qdata if qdata is not None else qp_instance(qn, qm, qp_, dt)
+    m0, n = (2 + qn) + qm + qp_, qn + 1
+    pad = (-m0) % 4
+    m = m0 + pad
+    stacked = np.zeros((m, n), dtype=dt, order="F")
+    stacked[1, :qn] = q; stacked[1, qn] = -1.0
+    idx = np.arange(qn, dtype=np.int64)
+    stacked[2 + idx, idx] = -psqrt[idx * (idx + 1) // 2 + idx]           # P is diagonal in these workloads
+    stacked[2 + qn:2 + qn + qm, :qn] = np.asarray(g).reshape(qm, qn, order="F")
+    stacked[2 + qn + qm:2 + qn + qm + qp_, :qn] = np.asarray(a_eq).reshape(qp_, qn, order="F")
+    b = np.zeros(m, dtype=dt); b[0] = 1.0; b[2 + qn:2 + qn + qm] = h; b[2 + qn + qm:2 + qn + qm + qp_] = b_eq
+    c = np.zeros(n, dtype=dt); c[qn] = 1.0
+    return stacked, b, c, pad
+
+
 # ------------------------------------------------------------------------------------------------------------
 def cpu_reference_leg(spec, steps, warmup, sample_blocks=None, threads=None):
     """The reference's CPU path for this workload: the oracle's port of the matching front-end + F64LAPACK (f64,
@@ -264,6 +284,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-blocks", type=int, default=None)
     ap.add_argument("--pair-fusion", type=int, default=1, help="serve op/trans_op pairs with one read of A when the backend can")
+    ap.add_argument("--route", default="fused", choices=["fused", "stock"],
+                    help="QP workloads: 'fused' = ProbQP's stacked operator as one dense A (DenseOp + ProductCone), "
+                         "'stock' = the ProbQP front-end itself (MatOp per block, stock cones)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -271,14 +294,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     spec = WORKLOADS[args.workload]
     is_qp = spec["kind"] == "qp"
+    qp_stock = is_qp and args.route == "stock"
+    qp_fused = is_qp and args.route == "fused"
     esize = 4 if args.dtype == "f32" else 8
     if is_qp:
         qn, qm, qp_ = spec["n"], spec["m"], spec["p"]
         m, n = (2 + qn) + qm + qp_, qn + 1                   # the stacked operator ProbQP builds (qp.rs:325-331)
-        dense_elems = qm * qn + qp_ * qn + qn * (qn + 1) // 2     # G + A_eq + packed P^(1/2): what one op / trans_op reads
-        config = {"workload": args.workload, "cone": "ConeRotSOC(%d) x ConeRPos(%d) x ConeZero(%d)" % (qn + 2, qm, qp_),
+        qpad = (-m) % 4 if qp_fused else 0                   # zero rows (extra ConeZero coordinates, b = 0) so columns start 16-byte aligned
+        dense_elems = qm * qn + qp_ * qn + qn * (qn + 1) // 2     # G + A_eq + packed P^(1/2): what one op / trans_op reads in the reference's formulation
+        config = {"workload": args.workload, "cone": "ConeRotSOC(%d) x ConeRPos(%d) x ConeZero(%d)" % (qn + 2, qm, qp_ + qpad),
                   "A": "%d x %d through ProbQP: G %d x %d + A_eq %d x %d dense column-major, P^(1/2) upper-packed %d x %d" % (m, n, qm, qn, qp_, qn, qn, qn),
-                  "route": "stock MatOp route (transform_ge + transform_sp per block, no pair fusion)"}
+                  "route": "stock MatOp route (the ProbQP front-end itself: transform_ge + transform_sp per block, stock cones, no pair fusion)" if qp_stock else
+                           "fused DenseOp + ProductCone handed to the unmodified Solver: ProbQP's rows [0; q^T,-1; -P^(1/2); G; A_eq] (qp.rs:325-331) stacked into "
+                           "one dense %d x %d A (%d zero rows appended for alignment); algorithmic bytes stay the reference formulation's (packed P^(1/2))" % (m + qpad, n, qpad)}
+        m += qpad
     else:
         cone, n = spec["cone"], spec["n"]
         m = cone_rows(cone)
@@ -329,13 +358,24 @@ def main():
         config["parallelism"] = "A row-sharded x%d on cone-block boundaries, vectors replicated" % world
 
     abuf = None
-    if is_qp:
+    if qp_stock:
         qdata = qp_instance(qn, qm, qp_, dt)
         m_loc = m
         matrix_h2d = dense_elems * esize            # wrapped host arrays: uploaded on first use inside Solver::solve
 
         def new_session():
             return host.Session.qp(dt, qdata[0], qdata[1], qdata[2], qdata[3], qdata[4], qdata[5], 1e-12, p_is_sqrt=True, col_major=True)
+    elif qp_fused:
+        m_loc, matrix_h2d = m, 0                    # the stacked A is uploaded once into a backend buffer before the timed regions
+        stacked, b, c, _ = qp_stacked(qn, qm, qp_, dt)
+        assert stacked.shape == (m, n)
+        abuf = capi.Buf(dtype=dt, length=m * n)
+        abuf.upload(stacked.reshape(-1, order="F"))
+        del stacked
+        blocks = [(capi.CONE_ROTSOC, qn + 2), (capi.CONE_RPOS, qm), (capi.CONE_ZERO, qp_ + qpad)]
+
+        def new_session():
+            return host.Session.dense(dt, abuf.view(), m, n, c, b, blocks, fused_op=True, fused_cone=True)
     else:
         from totsu_b200 import shard
         if cone[0] == "soc":
@@ -374,7 +414,7 @@ def main():
 
     # ---- device-resident timing: K iterations between two events on the library's stream
     s = new_session()
-    assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=not is_qp) == "None"
+    assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=not qp_stock) == "None"
     if os.environ.get("BENCH_DEBUG"):
         for _ in range(min(warmup, 5)):
             s.step(1)
@@ -410,7 +450,7 @@ def main():
     barrier()
     s = new_session()
     t0 = time.perf_counter()
-    st = s.begin(max_iter=steps, eps_acc=0.0, eps_inf=0.0, device_precond=not is_qp)
+    st = s.begin(max_iter=steps, eps_acc=0.0, eps_inf=0.0, device_precond=not qp_stock)
     assert st == "None"
     t1 = time.perf_counter()
     st, _ = s.run()
@@ -446,20 +486,19 @@ def main():
         vals = [v["dram_bytes_per_launch"] for k, v in tj.items() if k.startswith(args.workload + "|") and want in k]
         if vals:
             traffic = sum(vals) / len(vals)
-    local_elems = dense_elems if is_qp else m_loc * n
     if nl.value:
         # ALGORITHMIC bytes per launch: one read of this rank's dense block per op / trans_op served.  With
         # the lazy pairing a launch serves an op AND a trans_op from ONE read of A, so the algorithmic figure is twice the
         # bytes actually streamed and `frac` may exceed 1; `streamed_*` is the un-doubled DRAM-side figure.  (QP: the
         # launches timed are the transform_ge ones on G and A_eq; the packed P^(1/2) goes through spmv_kernel.)
         avg_ms = kms.value / nl.value
-        ge_elems = (qm * qn + qp_ * qn) if is_qp else m_loc * n
+        ge_elems = (qm * qn + qp_ * qn) if qp_stock else dense_elems if qp_fused else m_loc * n
         alg_per_launch = 6.0 * prof_iters * ge_elems * esize / nl.value
         ach = alg_per_launch / (avg_ms * 1e-3) / 1e9
         streamed = (kbytes.value / nl.value) / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "stream_kernel (TMA bulk-copy matvec)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture)" if traffic else None, "peak_source": peak_src, "launches_timed": int(nl.value), "avg_launch_ms": avg_ms,
-                "algorithmic_bytes_per_launch": alg_per_launch, "matvecs_per_launch": 6.0 * prof_iters * (2 if is_qp else 1) / nl.value,
+                "algorithmic_bytes_per_launch": alg_per_launch, "matvecs_per_launch": 6.0 * prof_iters * (2 if qp_stock else 1) / nl.value,
                 "streamed_bytes_per_launch": kbytes.value / nl.value, "streamed_gbs": streamed, "streamed_frac": streamed / peak,
                 "note": ("op/trans_op pairs share one read of A (lazy pairing behind tb_denseop_apply): achieved/frac use the un-fused "
                          "algorithmic bytes and can exceed 1; streamed_frac is bytes actually read / peak") if pairs_per_iter else None}
@@ -468,7 +507,7 @@ def main():
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "Solver::solve (begin + %d iterations + end) through the host layer, work/c/b%s in host memory" % (steps, " and the matrices" if is_qp else ""),
+                    "what": "Solver::solve (begin + %d iterations + end) through the host layer, work/c/b%s in host memory" % (steps, " and the matrices" if qp_stock else ""),
                     "breakdown_s": {"begin": t1 - t0, "iterate": t2 - t1, "end_and_readback": t0 + t_e2e_local - t2}},
             "gpu_launches": int(launches), "roofline": roof,
             "hbm_frac_whole_iteration": abytes_iter * value / (world * peak * 1e9),

@@ -336,3 +336,35 @@ def test_front_end_qp_iterates_match_oracle(dt, presqrt):
         ex, ey = H.rel_linf(xh, so.snapshots[k][0]), H.rel_linf(yh, so.snapshots[k][1])
         assert ex <= tol[k] and ey <= tol[k], (dt, presqrt, k, ex, ey)
     s.close()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_front_end_qp_matches_fused_dense(dt):
+    """bench.py's two routes for config C2 solve the same problem: the ProbQP front-end (stock MatOp route, packed
+    P^(1/2) through transform_sp) and its composite operator stacked into one dense A (fused DenseOp + ProductCone, two
+    zero rows appended for alignment) give the same iterates."""
+    import bench
+    qn, qm, qp_ = 64, 48, 7
+    qdata = bench.qp_instance(qn, qm, qp_, dt)
+    stacked, b, c, pad = bench.qp_stacked(qn, qm, qp_, dt, qdata)
+    m, n = stacked.shape
+    m0 = m - pad
+    s1 = host.Session.qp(dt, qdata[0], qdata[1], qdata[2], qdata[3], qdata[4], qdata[5], 1e-12, p_is_sqrt=True, col_major=True)
+    abuf, av = H.device_matrix(stacked)
+    blocks = [(ROTSOC, qn + 2), (RPOS, qm), (ZERO, qp_ + pad)]
+    s2 = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=True, fused_cone=True)
+    assert s1.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0) == "None"
+    assert s2.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+    tol = 1e-10 if dt == np.float64 else 2e-4
+    done = 0
+    for k in (1, 10, 60):
+        s1.step(k - done); s2.step(k - done); done = k
+        x1, y1 = s1.xy(); x2, y2 = s2.xy()
+        # x_hat = (x[n], y[m], s[m], tau): compare the real coordinates, skip the padded rows of the fused problem
+        def strip_x(x, mm):
+            return np.concatenate([x[:n], x[n:n + m0], x[n + mm:n + mm + m0], x[n + 2 * mm:]])
+        def strip_y(y, mm):
+            return np.concatenate([y[:n], y[n:n + m0], y[n + mm:]])
+        assert H.rel_linf(strip_x(x2, m), strip_x(x1, m0)) <= tol, (dt, k)
+        assert H.rel_linf(strip_y(y2, m), strip_y(y1, m0)) <= tol, (dt, k)
+    s1.close(); s2.close(); abuf.release()
