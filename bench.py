@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-blocks", type=int, default=None)
     ap.add_argument("--pair-fusion", type=int, default=1, help="serve op/trans_op pairs with one read of A when the backend can")
+    ap.add_argument("--vprog", type=int, default=1, help="run the small vector commands between streaming launches as one launch per batch (csrc/vprog.cu)")
     ap.add_argument("--route", default="fused", choices=["fused", "stock"],
                     help="QP workloads: 'fused' = ProbQP's stacked operator as one dense A (DenseOp + ProductCone), "
                          "'stock' = the ProbQP front-end itself (MatOp per block, stock cones)")
@@ -339,6 +340,7 @@ def main():
     capi.init(local_rank)
     L = capi.lib()
     capi.check(L.tb_set_pair_fusion(1 if args.pair_fusion else 0))
+    capi.check(L.tb_set_vprog(1 if args.vprog else 0))
     if world > 1:
         if is_qp or spec["cone"][0] == "psd":
             raise SystemExit("%s is a single-GPU configuration (a PSD block / the QP front-end does not shard)" % args.workload)
@@ -424,14 +426,24 @@ def main():
     s.step(warmup)
     barrier()
     clocks = Clocks(local_rank) if rank == 0 else None
+    vl0, vo0 = C.c_uint64(), C.c_uint64()
+    capi.check(L.tb_vprog_stats(C.byref(vl0), C.byref(vo0)))
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    hw_s, hw_n = C.c_double(), C.c_uint64()
+    capi.check(L.tb_host_wait_stats(C.byref(hw_s), C.byref(hw_n)))        # reset
     e0.record(stream)
+    th0 = time.perf_counter()
     s.step(steps)
+    capi.check(L.tb_flush())             # nothing recorded or parked may be left behind the closing event
+    th1 = time.perf_counter()
     e1.record(stream)
+    capi.check(L.tb_host_wait_stats(C.byref(hw_s), C.byref(hw_n)))
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = capi.launch_count() - l0
+    vl1, vo1 = C.c_uint64(), C.c_uint64()
+    capi.check(L.tb_vprog_stats(C.byref(vl1), C.byref(vo1)))
     clk = clocks.stop() if clocks else None
     last = s.last
     # ---- the same region again with per-launch events around the streaming matvec (roofline numerator)
@@ -512,6 +524,11 @@ def main():
             "gpu_launches": int(launches), "roofline": roof,
             "hbm_frac_whole_iteration": abytes_iter * value / (world * peak * 1e9),
             "algorithmic_bytes_per_iteration": abytes_iter, "pair_fusion": bool(args.pair_fusion), "pairs_fused_per_iteration": pairs_per_iter,
+            "vector_programs": {"enabled": bool(args.vprog), "launches_per_iteration": (vl1.value - vl0.value) / steps,
+                                "micro_ops_per_iteration": (vo1.value - vo0.value) / steps,
+                                "note": "small vector commands recorded into one cluster launch per batch (csrc/vprog.cu); each program counts as one of gpu_launches"},
+            "host": {"loop_s": th1 - th0, "waiting_for_device_s": hw_s.value, "host_visible_scalars_per_iteration": hw_n.value / steps,
+                     "note": "host time of the timed loop and the part of it spent spinning on device results: the rest is issuing launches"},
             "clocks": clk, "last_residuals": [last.c0, last.c1, last.c2], "status_e2e": st}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -64,6 +64,17 @@ int         tb_set_gemv_path(int mode);
  * queue first, so results are bit-identical to the unfused order.  0 restores launch-at-call behaviour. */
 int         tb_set_pair_fusion(int on);
 int         tb_pairs_fused(uint64_t* out);           /* pairs served by one pass since tb_init */
+/* Small vector commands (level-1 ops, vector operators, finalize steps, single-element get/set) are recorded and run as
+ * one launch per batch - a "vector program" (csrc/vprog.cu) - submitted when anything else uses the stream or a
+ * host-visible result is needed.  tb_set_vprog(0) launches one kernel per command instead (A/B, debugging);
+ * tb_flush submits whatever is pending (deferred dense applies and the recorded program) without waiting;
+ * tb_vprog_stats: programs launched / micro-ops recorded since tb_init. */
+int         tb_set_vprog(int on);
+int         tb_vprog_stats(uint64_t* launches, uint64_t* ops);
+int         tb_flush(void);
+/* diagnostics: host seconds spent waiting for host-visible scalars (and how many waits) since the last call; a host that
+ * never waits is launch-bound, one that mostly waits is device-bound */
+int         tb_host_wait_stats(double* seconds, uint64_t* waits);
 
 /* ---- buffers: the SliceLike role (slicelike.rs:23-69; totsu_f32cuda/src/f32cuda_slice.rs:215-309) ------- */
 /* SliceLike::new_ref / new_mut: wrap caller-owned host memory with a device mirror.  The host slice stays

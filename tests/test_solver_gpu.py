@@ -368,3 +368,40 @@ def test_front_end_qp_matches_fused_dense(dt):
         assert H.rel_linf(strip_x(x2, m), strip_x(x1, m0)) <= tol, (dt, k)
         assert H.rel_linf(strip_y(y2, m), strip_y(y1, m0)) <= tol, (dt, k)
     s1.close(); s2.close(); abuf.release()
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["socp", "qp_like", "stream"])
+def test_vector_programs_match_per_kernel_launches(name, dt):
+    """csrc/vprog.cu: recording the small vector commands into one launch per batch changes neither the order of
+    operations nor (beyond the double-precision accumulation of the dot products) the arithmetic: 40 iterations with
+    tb_set_vprog(1) and tb_set_vprog(0) agree to rounding, and the batched run really batches (>= 2 micro-ops per launch incl. set-up)."""
+    import ctypes as C
+    L = capi.lib()
+    blocks, n = SYN[name]()
+    m = sum(l for _, l in blocks)
+    a, b, c = H.make_instance(m, n, blocks, seed=5, dtype=dt)
+    abuf, av = H.device_matrix(a)
+    out = {}
+    try:
+        for on in (1, 0):
+            capi.check(L.tb_set_vprog(on))
+            v0, o0, v1, o1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+            capi.check(L.tb_vprog_stats(C.byref(v0), C.byref(o0)))
+            s = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=True, fused_cone=True)
+            assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+            s.step(40)
+            out[on] = s.xy() + ((s.last.c0, s.last.c1, s.last.c2),)
+            s.close()
+            capi.check(L.tb_vprog_stats(C.byref(v1), C.byref(o1)))
+            if on:
+                assert v1.value > v0.value and (o1.value - o0.value) >= 2 * (v1.value - v0.value)
+            else:
+                assert v1.value == v0.value
+    finally:
+        capi.check(L.tb_set_vprog(1))
+        abuf.release()
+    tol = 1e-12 if dt == np.float64 else 2e-5
+    assert H.rel_linf(out[1][0], out[0][0]) <= tol and H.rel_linf(out[1][1], out[0][1]) <= tol
+    for g, w in zip(out[1][2], out[0][2]):
+        assert (not np.isfinite(w) and (g == w or np.isnan(w))) or abs(g - w) <= 50 * tol * max(abs(w), 1e-3)

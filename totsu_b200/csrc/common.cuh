@@ -121,11 +121,22 @@ struct Cmd {
     tb_view x{0, 0, 0}, y{0, 0, 0};
 };
 
+// The library's stream.  Reading it as a cudaStream_t (every kernel launch, copy, synchronisation, NCCL call) first
+// submits the vector program recorded so far (vprog.cu), so recorded micro-ops can never be overtaken; `.raw` is the
+// handle itself.
+void vp_flush();
+struct StreamRef {
+    cudaStream_t raw = nullptr;
+    operator cudaStream_t() const { vp_flush(); return raw; }
+};
+
 struct Context {
     bool inited = false;
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    StreamRef stream;
+    bool vprog = true;                   // record small vector kernels into one launch (vprog.cu); tb_set_vprog
+    uint64_t vprog_launches = 0, vprog_ops = 0;
     std::vector<Buffer> bufs;            // handle = index + 1
     std::vector<int64_t> free_ids;
     // scratch for two-stage (deterministic) reductions / matvec partials
@@ -141,6 +152,8 @@ struct Context {
     volatile double* hostbox = nullptr;
     double* hostbox_dev = nullptr;       // device alias of hostbox
     uint64_t box_seq = 0;
+    double box_wait_s = 0.0;             // host time spent spinning on the box since the last tb_host_wait_stats
+    uint64_t box_waits = 0;
     // slab for tiny buffers (the solver wraps a 1-element slice every iteration: solver.rs:590-591)
     char* small_slab = nullptr;
     std::vector<int> small_free;

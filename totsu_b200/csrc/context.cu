@@ -4,7 +4,9 @@
 // slice, range-based dirty tracking instead of a per-split state machine + HashMap, a slab for the tiny
 // 1-element slices the solver wraps every iteration, and a pinned mailbox for host-visible scalars.
 #include "common.cuh"
+#include "vprog.cuh"
 #include <cstdlib>
+#include <chrono>
 
 namespace tb {
 
@@ -49,6 +51,10 @@ uint64_t box_next() { return ++ctx().box_seq; }
 double box_wait(uint64_t seq) {
     Context& c = ctx();
     volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(c.hostbox + 1);
+    struct Timer {      // host time spent waiting for the device: tells a launch-bound host from a busy device (tb_host_wait_stats)
+        Context& c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Timer() { c.box_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); c.box_waits += 1; }
+    } timer{c};
     for (unsigned long long spins = 0;; ++spins) {
         if (*flag == seq) break;
         if ((spins & 0xFFFF) == 0xFFFF) {
@@ -160,10 +166,14 @@ template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
         *out = reinterpret_cast<const T*>(b.host)[i];
         return;
     }
-    const uint64_t seq = box_next();
-    fetch1_kernel<T><<<1, 1, 0, c.stream>>>(reinterpret_cast<const T*>(b.dev + i * b.esize), c.hostbox_dev, seq);
-    TB_LAUNCH_CHECK();
-    *out = (T)box_wait(seq);            // T -> double -> T is exact
+    if (vp_enabled()) {
+        *out = (T)vp_fetch_to_host(DT<T>::id, b.dev + i * b.esize);      // last micro-op of the pending vector program
+    } else {
+        const uint64_t seq = box_next();
+        fetch1_kernel<T><<<1, 1, 0, c.stream>>>(reinterpret_cast<const T*>(b.dev + i * b.esize), c.hostbox_dev, seq);
+        TB_LAUNCH_CHECK();
+        *out = (T)box_wait(seq);            // T -> double -> T is exact
+    }
     if (b.host && b.host_mut) {      // like SliceLike::get -> get_ref on the 1-element split: host copy becomes current
         reinterpret_cast<T*>(b.host)[i] = *out;
         b.dev_newer.sub(i, i + 1);
@@ -175,8 +185,12 @@ template <typename T> static void set1(const tb_view& v, size_t idx, T val) {
     TB_REQUIRE(idx < v.len, "index out of range");
     tb_view one{v.buf, v.off + idx, 1};
     T* p = wptr<T>(one, true);
-    set1_kernel<T><<<1, 1, 0, ctx().stream>>>(p, val);
-    TB_LAUNCH_CHECK();
+    if (vp_enabled()) {
+        vp_set1(DT<T>::id, p, (double)val);
+    } else {
+        set1_kernel<T><<<1, 1, 0, ctx().stream>>>(p, val);
+        TB_LAUNCH_CHECK();
+    }
     Buffer& b = get_buf(v.buf);
     if (b.host && b.host_mut) {      // write-through: both copies agree, a following get() needs no device round trip
         reinterpret_cast<T*>(b.host)[v.off + idx] = val;
@@ -208,7 +222,8 @@ int tb_init(int device) {
         if (prop.major < 10) fail(TB_ERR_UNSUPPORTED, std::string("totsu_b200 is built for sm_100a (B200); found ") + prop.name);
         c.device = device;
         c.sm_count = prop.multiProcessorCount;
-        TB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        TB_CUDA(cudaStreamCreateWithFlags(&c.stream.raw, cudaStreamNonBlocking));
+        vp_init();
         TB_CUDA(cudaHostAlloc(&c.mailbox_host, 64 * sizeof(double), cudaHostAllocDefault));
         TB_CUDA(cudaMalloc(&c.mailbox_dev, 64 * sizeof(double)));
         TB_CUDA(cudaMalloc(&c.tickets, (64 + Context::kTicketPool) * sizeof(unsigned int)));
@@ -254,8 +269,9 @@ int tb_shutdown(void) {
         cudaFree(c.mailbox_dev);
         cudaFree(c.tickets);
         cudaFree(c.small_slab);
-        cudaStreamDestroy(c.stream);
-        c.stream = nullptr;
+        vp_shutdown();
+        cudaStreamDestroy(c.stream.raw);
+        c.stream.raw = nullptr;
         c.inited = false;
     });
 }
@@ -273,7 +289,7 @@ int tb_device_sync(void) {
 int tb_get_stream(void** out) {
     return api([&] {
         require_init();
-        *out = (void*)ctx().stream;
+        *out = (void*)(cudaStream_t)ctx().stream;
     });
 }
 
@@ -292,6 +308,28 @@ int tb_set_pair_fusion(int on) {
     return api([&] { ctx().pair_fusion = on != 0; });
 }
 
+int tb_set_vprog(int on) {
+    return api([&] {
+        require_init();
+        vp_flush();
+        ctx().vprog = on != 0;
+    });
+}
+int tb_vprog_stats(uint64_t* launches, uint64_t* ops) {
+    return api_raw([&] { *launches = ctx().vprog_launches; *ops = ctx().vprog_ops; });
+}
+int tb_flush(void) {
+    return api([&] {
+        require_init();
+        vp_flush();
+    });
+}
+int tb_host_wait_stats(double* seconds, uint64_t* waits) {
+    return api_raw([&] {
+        *seconds = ctx().box_wait_s; *waits = ctx().box_waits;
+        ctx().box_wait_s = 0.0; ctx().box_waits = 0;
+    });
+}
 int tb_pairs_fused(uint64_t* out) {
     return api([&] { *out = ctx().pairs_fused; });
 }

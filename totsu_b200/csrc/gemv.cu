@@ -22,6 +22,7 @@
 // leading dimension / base address is not 16-byte aligned (e.g. the 63 x n blocks of ProbSOCP) or that are
 // too small to be worth a persistent launch.  Same two-stage deterministic reduction.
 #include "common.cuh"
+#include "vprog.cuh"
 
 namespace tb {
 
@@ -41,6 +42,7 @@ __global__ void finalize_kernel(const T* __restrict__ part, int nparts, size_t l
 
 template <typename T> void l2_finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
     if (len == 0) return;
+    if (vp_enabled(len)) { vp_finalize(DT<T>::id, part, nparts, ld, len, (double)alpha, (double)beta, y); return; }
     int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
     finalize_kernel<T><<<g, 256, 0, ctx().stream>>>(part, nparts, ld, len, alpha, beta, y);
     TB_LAUNCH_CHECK();
@@ -75,6 +77,11 @@ static void finalize2(const T* part_a, int nparts_a, size_t ld_a, size_t len_a, 
                       const T* part_b, int nparts_b, size_t ld_b, size_t len_b, T alpha_b, T beta_b, T* y_b) {
     const size_t len = len_a + len_b;
     if (len == 0) return;
+    if (vp_enabled(std::max(len_a, len_b))) {     // two independent micro-ops: no barrier between them
+        if (len_a) vp_finalize(DT<T>::id, part_a, nparts_a, ld_a, len_a, (double)alpha_a, (double)beta_a, y_a);
+        if (len_b) vp_finalize(DT<T>::id, part_b, nparts_b, ld_b, len_b, (double)alpha_b, (double)beta_b, y_b);
+        return;
+    }
     int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
     finalize2_kernel<T><<<g, 256, 0, ctx().stream>>>(part_a, nparts_a, ld_a, len_a, alpha_a, beta_a, y_a, part_b, nparts_b, ld_b, len_b, alpha_b, beta_b, y_b);
     TB_LAUNCH_CHECK();
@@ -199,6 +206,10 @@ template <typename T, bool ABS>
 static void run_generic_n(const T* A, size_t lda, size_t n_row, size_t n_col, const T* x, T alpha, T beta, T* y) {
     Context& c = ctx();
     if (n_row == 0) return;
+    if (!ABS && n_col == 1 && vp_enabled(n_row)) {       // an n x 1 operator applied to a device scalar: y = alpha * A * x[0] + beta * y
+        vp_axs(DT<T>::id, (double)alpha, A, x, (double)beta, y, n_row);
+        return;
+    }
     size_t row_blocks = (n_row + 127) / 128;
     size_t want = ((size_t)c.sm_count * 2 + row_blocks - 1) / row_blocks;
     size_t max_splits = std::max<size_t>(1, n_col / 64);
@@ -222,6 +233,10 @@ template <typename T, bool ABS>
 static void run_generic_t(const T* A, size_t lda, size_t n_row, size_t n_col, const T* x, T alpha, T beta, T* y) {
     Context& c = ctx();
     if (n_col == 0) return;
+    if (!ABS && n_col == 1 && n_row > 0 && vp_enabled(n_row)) {     // the transposed n x 1 operator: a dot product into y[0]
+        vp_dot(DT<T>::id, (double)alpha, A, x, n_row, (double)beta, y);
+        return;
+    }
     size_t col_groups = (n_col + 7) / 8;
     size_t want = ((size_t)c.sm_count * 2 + col_groups - 1) / col_groups;
     size_t max_splits = std::max<size_t>(1, n_row / 1024);
