@@ -90,8 +90,10 @@ def test_transform_ge_auto_path_and_errors(dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("n", [1, 2, 5, 16, 17, 100, 513, 2050])
+@pytest.mark.parametrize("n", [1, 2, 5, 16, 17, 100, 511, 512, 513, 1024, 1025, 2050, 4099, 6000])
 def test_transform_sp(dt, n):
+    """n < 512 (and unaligned views): generic kernel; n >= 512: the TMA streaming kernel (sizes chosen so that the
+    packed length leaves 0..3 trailing elements outside the last aligned 16-byte window, and chunks are ragged)."""
     rng = np.random.default_rng(n)
     sp = rng.standard_normal(n * (n + 1) // 2).astype(dt)
     x = rng.standard_normal(n).astype(dt)
@@ -276,3 +278,28 @@ def test_full_size_properties_c5_single_gpu():
     assert rel_linf(atu[cols], subc.T @ u.astype(np.float64)) <= 5e-5
     capi.check(L.tb_denseop_destroy(h.value))
     abuf.release()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_transform_sp_unaligned_view_and_engines_agree(dt):
+    """The packed matrix as a sub-view that is not 16-byte aligned falls back to the generic kernel; both kernels agree
+    with each other (tb_set_gemv_path(1) forces the generic one)."""
+    n = 1500
+    rng = np.random.default_rng(3)
+    sp = rng.standard_normal(n * (n + 1) // 2 + 1).astype(dt)
+    x = rng.standard_normal(n).astype(dt)
+    res = []
+    for off, path in ((0, 0), (1, 0), (0, 1)):
+        capi.check(capi.lib().tb_set_gemv_path(path))
+        y = np.zeros(n, dtype=dt)
+        sb, xb, yb = capi.Buf(sp.copy(), mutable=False), capi.Buf(x.copy(), mutable=False), capi.Buf(y)
+        capi.check(capi.fn("tb_transform_sp", dt)(n, 1.0, sb.view(off, n * (n + 1) // 2), xb.view(), 0.0, yb.view()))
+        for b in (sb, xb, yb):
+            b.release()
+        ry = np.zeros(n)
+        O.F64LAPACK.transform_sp(n, 1.0, sp[off:off + n * (n + 1) // 2].astype(np.float64), x.astype(np.float64), 0.0, ry)
+        scale = np.abs(ry).max() + np.abs(sp).max() * np.abs(x).sum()
+        assert np.abs(y - ry).max() <= (3e-6 if dt == np.float32 else 1e-13) * scale, (off, path)
+        res.append(y)
+    capi.check(capi.lib().tb_set_gemv_path(0))
+    assert np.abs(res[0].astype(np.float64) - res[2].astype(np.float64)).max() <= (1e-5 if dt == np.float32 else 1e-12) * np.abs(res[0]).max()

@@ -9,6 +9,8 @@
 //     y[c] += a*x[r]   (per-thread per-column accumulators, block-reduced once per CTA)
 // plus the diagonal.  Per-CTA partial vectors go to scratch and a finalize kernel adds them in fixed order.
 #include "common.cuh"
+#include "ptx.cuh"
+#include <map>
 
 namespace tb {
 
@@ -93,6 +95,364 @@ __global__ void spmv_finalize(const T* __restrict__ part_r, const T* __restrict_
     y[i] = r;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Streaming path: the packed triangle read once at HBM speed.
+//
+// Same machine as gemv.cu's stream_kernel (persistent CTAs, one producer warp feeding a 6-stage shared-memory ring with
+// TMA bulk copies, 8 consumer warps), adapted to the packed layout: column c is the contiguous run S[0..c, c] at
+// element c(c+1)/2.  The triangle is cut into row chunks of TR rows and column tiles of 8; a tile of chunk R holds, for
+// each of its columns, the segment rows [R*TR, min((R+1)*TR, c+1)).  A segment starts at an arbitrary element, so the
+// producer copies the enclosing 16-byte-aligned window (<= VEC-1 elements of slack on each side, still inside the array)
+// and the consumers index it with the per-column shift.  Every staged element a = S[r,c] is used twice while it is in
+// shared memory: y[r] += a x[c] (thread-owned rows, r < c) and y[c] += a x[r] (one warp per column, r <= c).
+// Work units (chunk, tile range) are sized to ~4 per CTA and dealt to CTAs by cumulative bytes (the triangle makes
+// chunks unequal).  Partials go to scratch; spmv_stream_finalize adds them in a fixed order: no atomics.
+// The last total % VEC elements of the array cannot be fetched by an aligned window without reading past the end; the
+// finalize kernel adds their (<= 3) contributions directly.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SPS_WARPS = 8;
+constexpr int SPS_CONSUMERS = SPS_WARPS * 32;
+constexpr int SPS_THREADS = SPS_CONSUMERS + 32;
+constexpr int SPS_TC = 8;               // columns per tile
+constexpr int SPS_MAX_UNIT_COLS = 2048;
+constexpr size_t SPS_XRES_BYTES = 49152;     // x resident in shared memory up to this size
+
+struct SpUnit { int chunk, split, tile0, tile1; };
+
+// Shift of column c's segment inside its 16-byte-aligned window: (c(c+1)/2 + row0) mod VEC.  row0 is a multiple of VEC and
+// a tile starts at a multiple of 8, so the shift depends only on the column's slot j = c mod 8 in the tile:
+// c(c+1)/2 mod 4 = {0,1,3,2,2,3,1,0}[c mod 8], c(c+1)/2 mod 2 = {0,1,1,0}[c mod 4].
+template <int VEC> __host__ __device__ constexpr int sp_shift(int j) {
+    return VEC == 4 ? ((j * (j + 1) / 2) & 3) : ((j * (j + 1) / 2) & 1);
+}
+struct SpParams {
+    const void* S;
+    size_t n, total;
+    const void* x;
+    void* part_n;            // [max_splits][n]
+    void* part_t;            // [n_chunks][n]
+    const SpUnit* units;
+    const int* cta_begin;    // [gridDim.x + 1]
+    int tail;                // trailing elements of the array left to the finalize kernel
+};
+
+// XRES: all of x lives in shared memory for the whole kernel (n * sizeof(T) <= 48 KB, one ring stage fewer); otherwise each
+// work unit stages the x slice of its columns and re-reads the x of its rows from L2.
+template <typename T, bool XRES>
+__global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpParams p) {
+    constexpr int SPS_STAGES = XRES ? 5 : 6;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int TR = SPS_CONSUMERS * VEC;          // rows per chunk: 1024 (f32) / 512 (f64)
+    constexpr int SLOT = TR + VEC;                   // staged elements per column: the aligned window may start VEC-1 early
+    constexpr int STAGE_ELEMS = SPS_TC * SLOT;
+    constexpr int KT = TR / 32;                      // rows per lane in the column pass
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* stage_base = reinterpret_cast<T*>(smem_raw);
+    T* xs = stage_base + (size_t)SPS_STAGES * STAGE_ELEMS;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(xs + (XRES ? SPS_XRES_BYTES / sizeof(T) : (size_t)SPS_MAX_UNIT_COLS));
+    uint64_t* empty_bar = full_bar + SPS_STAGES;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T* __restrict__ S = reinterpret_cast<const T*>(p.S);
+    const size_t n = p.n;
+    if (tid == 0) {
+        for (int s = 0; s < SPS_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], SPS_WARPS); }
+        ptx::mbar_fence_init();
+    }
+    __syncthreads();
+    const int u_begin = p.cta_begin[blockIdx.x], u_end = p.cta_begin[blockIdx.x + 1];
+    const size_t last_lim = n - (size_t)p.tail;      // exclusive row limit of the last column
+    if (XRES && warp < SPS_WARPS) {
+        const T* __restrict__ xg = reinterpret_cast<const T*>(p.x);
+        for (size_t i = tid; i < n; i += SPS_CONSUMERS) xs[i] = xg[i];
+        ptx::named_bar_sync(1, SPS_CONSUMERS);
+    }
+
+    if (warp == SPS_WARPS) {
+        // ===================== producer warp =====================
+        const uint64_t pol = ptx::policy_evict_first();
+        int s = 0;
+        uint32_t phase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            const SpUnit un = p.units[u];
+            const size_t row0 = (size_t)un.chunk * TR;
+            for (int t = un.tile0; t < un.tile1; ++t) {
+                const size_t c = (size_t)t * SPS_TC + lane;
+                uint32_t bytes = 0;
+                const T* src = nullptr;
+                if (lane < SPS_TC && c < n) {
+                    const size_t rlim = c == n - 1 ? last_lim : c + 1;
+                    if (rlim > row0) {
+                        const size_t len = rlim - row0 < (size_t)TR ? rlim - row0 : (size_t)TR;
+                        const size_t e = c * (c + 1) / 2 + row0;
+                        const size_t sh = e % VEC;
+                        src = S + (e - sh);
+                        bytes = (uint32_t)(((sh + len + VEC - 1) / VEC) * VEC * sizeof(T));
+                    }
+                }
+                const uint32_t tile_bytes = __reduce_add_sync(0xffffffffu, bytes);
+                ptx::mbar_wait(&empty_bar[s], phase ^ 1);
+                if (lane == 0) ptx::mbar_expect_tx(&full_bar[s], tile_bytes);
+                __syncwarp();
+                if (bytes) ptx::bulk_g2s(stage_base + (size_t)s * STAGE_ELEMS + (size_t)lane * SLOT, src, bytes, &full_bar[s], pol);
+                if (++s == SPS_STAGES) { s = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== consumer warps =====================
+        const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+        T* __restrict__ part_n = reinterpret_cast<T*>(p.part_n);
+        T* __restrict__ part_t = reinterpret_cast<T*>(p.part_t);
+        int s = 0;
+        uint32_t phase = 0;
+        for (int u = u_begin; u < u_end; ++u) {
+            const SpUnit un = p.units[u];
+            const size_t row0 = (size_t)un.chunk * TR;
+            const size_t c0 = (size_t)un.tile0 * SPS_TC;
+            const size_t c1 = (size_t)un.tile1 * SPS_TC < n ? (size_t)un.tile1 * SPS_TC : n;
+            const int ucols = (int)(c1 - c0);
+            if (!XRES) {
+                // stage x[c] of this unit's columns (the previous unit's readers are done: barrier first)
+                ptx::named_bar_sync(1, SPS_CONSUMERS);
+                for (int i = tid; i < ucols; i += SPS_CONSUMERS) xs[i] = x[c0 + i];
+                ptx::named_bar_sync(1, SPS_CONSUMERS);
+            }
+            const T* xcol = XRES ? xs + c0 : xs;      // x of the unit's columns, indexed from the unit's first column
+            // column pass: x of the rows this lane strides over (rows lane + 32 k of the chunk)
+            T xr[KT];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                const size_t r = row0 + lane + 32 * k;
+                xr[k] = r < n ? (XRES ? xs[r] : x[r]) : T(0);
+            }
+            // row pass: thread t owns rows t + 256 i of the chunk (conflict-free scalar LDS)
+            T acc[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = T(0);
+
+            int cl = 0;
+            for (int t = un.tile0; t < un.tile1; ++t, cl += SPS_TC) {
+                const size_t ct = (size_t)t * SPS_TC;
+                const int ncols = (int)(n - ct < (size_t)SPS_TC ? n - ct : (size_t)SPS_TC);
+                ptx::mbar_wait(&full_bar[s], phase);
+                const T* tile = stage_base + (size_t)s * STAGE_ELEMS;
+                const long long d0 = (long long)ct - (long long)row0;           // local row of column ct's diagonal element
+                if (d0 >= (long long)TR && ct + SPS_TC < n) {
+                    // right of the chunk's diagonal block and without the last column: every staged row counts, no masks
+#pragma unroll
+                    for (int j = 0; j < SPS_TC; ++j) {
+                        const T* col = tile + (size_t)j * SLOT + sp_shift<VEC>(j);
+                        const T xv = xcol[cl + j];
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) acc[i] += col[tid + SPS_CONSUMERS * i] * xv;
+                    }
+                    const T* col = tile + (size_t)warp * SLOT + sp_shift<VEC>(warp);
+                    T sum0 = T(0), sum1 = T(0), sum2 = T(0), sum3 = T(0);
+#pragma unroll
+                    for (int k = 0; k < KT; k += 4) {
+                        sum0 += col[lane + 32 * k] * xr[k];
+                        sum1 += col[lane + 32 * (k + 1)] * xr[k + 1];
+                        sum2 += col[lane + 32 * (k + 2)] * xr[k + 2];
+                        sum3 += col[lane + 32 * (k + 3)] * xr[k + 3];
+                    }
+                    const T sum = tbd::warp_sum((sum0 + sum1) + (sum2 + sum3));
+                    if (lane == 0) part_t[(size_t)un.chunk * n + ct + warp] = sum;
+                } else {
+                    // per-column limits in chunk-local rows: rows < lim_t are staged (column pass), rows < lim_n also skip the
+                    // diagonal (row pass); right of the chunk's diagonal block both are >= TR and mask nothing
+    #pragma unroll
+                    for (int j = 0; j < SPS_TC; ++j) {
+                        if (j < ncols) {
+                            const size_t c = ct + j;
+                            long long lim_t = d0 + j + 1;
+                            if (c == n - 1) lim_t = (long long)last_lim - (long long)row0;
+                            long long lim_n64 = lim_t < d0 + j ? lim_t : d0 + j;
+                            const int lim_n = lim_n64 > (long long)TR ? TR : (int)lim_n64;
+                            const T* col = tile + (size_t)j * SLOT + sp_shift<VEC>(j);
+                            const T xv = xcol[cl + j];
+    #pragma unroll
+                            for (int i = 0; i < VEC; ++i)
+                                if (warp * 32 + SPS_CONSUMERS * i < lim_n) {       // warp-uniform skip of rows below the diagonal
+                                    if (tid + SPS_CONSUMERS * i < lim_n) acc[i] += col[tid + SPS_CONSUMERS * i] * xv;
+                                }
+                        }
+                    }
+                    if (warp < ncols) {
+                        const size_t c = ct + warp;
+                        long long lim_t = d0 + warp + 1;
+                        if (c == n - 1) lim_t = (long long)last_lim - (long long)row0;
+                        const T* col = tile + (size_t)warp * SLOT + sp_shift<VEC>(warp);
+                        T sum0 = T(0), sum1 = T(0), sum2 = T(0), sum3 = T(0);
+                        const int lim = lim_t > (long long)TR ? TR : (int)lim_t;
+    #pragma unroll
+                        for (int k = 0; k < KT; k += 4) {
+                            if (32 * k >= lim) break;                 // warp-uniform: nothing staged below the diagonal
+                            if (lane + 32 * k < lim) sum0 += col[lane + 32 * k] * xr[k];
+                            if (lane + 32 * (k + 1) < lim) sum1 += col[lane + 32 * (k + 1)] * xr[k + 1];
+                            if (lane + 32 * (k + 2) < lim) sum2 += col[lane + 32 * (k + 2)] * xr[k + 2];
+                            if (lane + 32 * (k + 3) < lim) sum3 += col[lane + 32 * (k + 3)] * xr[k + 3];
+                        }
+                        const T sum = tbd::warp_sum((sum0 + sum1) + (sum2 + sum3));
+                        if (lane == 0) part_t[(size_t)un.chunk * n + c] = sum;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty_bar[s]);
+                if (++s == SPS_STAGES) { s = 0; phase ^= 1; }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const size_t r = row0 + tid + SPS_CONSUMERS * i;
+                if (r < n) part_n[(size_t)un.split * n + r] = acc[i];
+            }
+        }
+    }
+}
+
+// y[i] = alpha * ( sum_{s < splits(chunk(i))} part_n[s][i] + sum_{R <= chunk(i)} part_t[R][i] + tail terms ) + beta * y[i]
+// A CTA of 256 threads finishes 32 outputs: thread (w, lane) adds partials w, w + 8, ... of output lane, then the 8
+// sub-sums are added in a fixed order.
+template <typename T>
+__global__ void __launch_bounds__(256) spmv_stream_finalize(const T* __restrict__ part_n, const T* __restrict__ part_t, const T* __restrict__ S,
+                                                            const T* __restrict__ x, size_t n, size_t total, int tail, int tiles_per_unit,
+                                                            T alpha, T beta, T* y) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr size_t TR = (size_t)SPS_CONSUMERS * VEC;
+    __shared__ T red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t i = blockIdx.x * (size_t)32 + lane;
+    T v = T(0);
+    if (i < n) {
+        const size_t chunk = i / TR;
+        const size_t n_tiles = (n + SPS_TC - 1) / SPS_TC;
+        const size_t tiles_r = n_tiles - chunk * (TR / SPS_TC);
+        const size_t splits = (tiles_r + tiles_per_unit - 1) / tiles_per_unit;
+        for (size_t s = w; s < splits; s += 8) v += part_n[s * n + i];
+        for (size_t r = w; r <= chunk; r += 8) v += part_t[r * n + i];
+    }
+    red[w][lane] = v;
+    __syncthreads();
+    if (w == 0 && i < n) {
+        T tot = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) tot += red[k][lane];
+        if (tail > 0) {
+            const size_t lo = n - (size_t)tail;             // rows [lo, n) of the last column
+            const T* lastcol = S + (total - n);
+            if (i >= lo && i + 1 < n) tot += lastcol[i] * x[n - 1];
+            if (i + 1 == n) {
+                T t = T(0);
+                for (size_t r = lo; r < n; ++r) t += lastcol[r] * x[r];
+                tot += t;
+            }
+        }
+        T r = alpha * tot;
+        if (beta != T(0)) r += beta * y[i];
+        y[i] = r;
+    }
+}
+
+struct SpPlan {
+    SpUnit* units_dev = nullptr;
+    int* cta_begin_dev = nullptr;
+    int grid = 0, max_splits = 0, n_chunks = 0, tiles_per_unit = 0;
+};
+
+template <typename T> static const SpPlan& spmv_plan(size_t n) {
+    static std::map<size_t, SpPlan> cache;
+    auto it = cache.find(n);
+    if (it != cache.end()) return it->second;
+    constexpr size_t VEC = 16 / sizeof(T);
+    constexpr size_t TR = (size_t)SPS_CONSUMERS * VEC;
+    const size_t n_tiles = (n + SPS_TC - 1) / SPS_TC, n_chunks = (n + TR - 1) / TR;
+    size_t total_tiles = 0;
+    for (size_t R = 0; R < n_chunks; ++R) total_tiles += n_tiles - R * (TR / SPS_TC);
+    const size_t n_cta = (size_t)ctx().sm_count;
+    const size_t per_cta = n * sizeof(T) <= SPS_XRES_BYTES ? 4 : 2;      // units are cheap when x is resident in shared memory
+    size_t tpu = (total_tiles + per_cta * n_cta - 1) / (per_cta * n_cta);
+    tpu = std::max<size_t>(1, std::min<size_t>(tpu, SPS_MAX_UNIT_COLS / SPS_TC));
+    std::vector<SpUnit> units;
+    std::vector<double> weight;
+    size_t max_splits = 0;
+    for (size_t R = 0; R < n_chunks; ++R) {
+        const size_t t_start = R * (TR / SPS_TC), row0 = R * TR;
+        size_t split = 0;
+        for (size_t t0 = t_start; t0 < n_tiles; t0 += tpu, ++split) {
+            const size_t t1 = std::min(n_tiles, t0 + tpu);
+            units.push_back(SpUnit{(int)R, (int)split, (int)t0, (int)t1});
+            // consumer cost, not bytes, is what a unit takes: a tile cut by the diagonal (or holding the last column) runs the
+            // masked path, measured ~3x the instructions of a dense tile (ncu, profiles/r01_spmv_stream_full.md)
+            double w = 0.0;
+            for (size_t t = t0; t < t1; ++t) {
+                const size_t ct = t * SPS_TC;
+                const bool dense = ct >= row0 + TR && ct + SPS_TC < n;
+                w += dense ? 1.0 : 3.0;
+            }
+            weight.push_back(w);
+        }
+        max_splits = std::max(max_splits, split);
+    }
+    const int grid = (int)std::min<size_t>(n_cta, units.size());
+    std::vector<int> cta_begin((size_t)grid + 1, 0);
+    double tot = 0.0;
+    for (double w : weight) tot += w;
+    double cum = 0.0;
+    size_t u = 0;
+    for (int b = 0; b < grid; ++b) {
+        cta_begin[(size_t)b] = (int)u;
+        const double target = tot * (double)(b + 1) / (double)grid;
+        while (u < units.size() && cum + 0.5 * weight[u] <= target) { cum += weight[u]; ++u; }
+    }
+    cta_begin[(size_t)grid] = (int)units.size();      // the last CTA takes whatever the midpoint rule left over
+    SpPlan pl;
+    TB_CUDA(cudaMalloc(&pl.units_dev, units.size() * sizeof(SpUnit)));
+    TB_CUDA(cudaMalloc(&pl.cta_begin_dev, cta_begin.size() * sizeof(int)));
+    TB_CUDA(cudaMemcpy(pl.units_dev, units.data(), units.size() * sizeof(SpUnit), cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemcpy(pl.cta_begin_dev, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+    pl.grid = grid; pl.max_splits = (int)max_splits; pl.n_chunks = (int)n_chunks; pl.tiles_per_unit = (int)tpu;
+    return cache.emplace(n, pl).first->second;
+}
+
+template <typename T> static bool spmv_stream_eligible(const T* S, size_t n) {
+    if (ctx().gemv_mode == 1) return false;                          // tb_set_gemv_path(1): generic kernels only
+    return (reinterpret_cast<uintptr_t>(S) & 15) == 0 && n >= 512;
+}
+
+template <typename T> static void spmv_stream(size_t n, T alpha, const T* S, const T* x, T beta, T* y) {
+    Context& c = ctx();
+    constexpr size_t VEC = 16 / sizeof(T);
+    constexpr size_t TR = (size_t)SPS_CONSUMERS * VEC;
+    const SpPlan& pl = spmv_plan<T>(n);
+    const size_t total = n * (n + 1) / 2;
+    size_t bytes_n = (size_t)pl.max_splits * n * sizeof(T);
+    bytes_n = (bytes_n + 255) & ~size_t(255);
+    const size_t bytes_t = (size_t)pl.n_chunks * n * sizeof(T);
+    char* sc = reinterpret_cast<char*>(scratch(bytes_n + bytes_t));
+    SpParams p;
+    p.S = S; p.n = n; p.total = total; p.x = x;
+    p.part_n = sc; p.part_t = sc + bytes_n;
+    p.units = pl.units_dev; p.cta_begin = pl.cta_begin_dev;
+    p.tail = (int)(total % VEC);
+    const bool xres = n * sizeof(T) <= SPS_XRES_BYTES;
+    const size_t stages = xres ? 5 : 6;
+    const size_t x_elems = xres ? SPS_XRES_BYTES / sizeof(T) : (size_t)SPS_MAX_UNIT_COLS;
+    const size_t smem = stages * SPS_TC * (TR + VEC) * sizeof(T) + x_elems * sizeof(T) + 2 * stages * sizeof(uint64_t) + 128;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[xres ? 1 : 0]) {
+        if (xres) TB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else TB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[xres ? 1 : 0] = true;
+    }
+    if (xres) spmv_stream_kernel<T, true><<<pl.grid, SPS_THREADS, smem, c.stream>>>(p);
+    else spmv_stream_kernel<T, false><<<pl.grid, SPS_THREADS, smem, c.stream>>>(p);
+    TB_LAUNCH_CHECK();
+    spmv_stream_finalize<T><<<(unsigned)((n + 31) / 32), 256, 0, c.stream>>>(reinterpret_cast<const T*>(p.part_n), reinterpret_cast<const T*>(p.part_t), S, x,
+                                                                              n, total, p.tail, pl.tiles_per_unit, alpha, beta, y);
+    TB_LAUNCH_CHECK();
+}
+
 template <typename T> static void api_transform_sp(size_t n, T alpha, tb_view mat, tb_view x, T beta, tb_view y) {
     require_init();
     TB_REQUIRE(mat.len == n * (n + 1) / 2, "transform_sp: mat.len != n(n+1)/2");     // f64lapack.rs:151
@@ -101,6 +461,7 @@ template <typename T> static void api_transform_sp(size_t n, T alpha, tb_view ma
     const T* px = rptr<T>(x);
     T* py = wptr<T>(y, beta == T(0));
     if (n == 0) return;
+    if (spmv_stream_eligible<T>(S, n)) { spmv_stream<T>(n, alpha, S, px, beta, py); return; }
     Context& c = ctx();
     const size_t n_panels = (n + SP_PANEL - 1) / SP_PANEL;
     const size_t n_chunks = (n + SP_ROWS - 1) / SP_ROWS;
