@@ -72,6 +72,12 @@ int         tb_pairs_fused(uint64_t* out);           /* pairs served by one pass
 int         tb_set_vprog(int on);
 int         tb_vprog_stats(uint64_t* launches, uint64_t* ops);
 int         tb_flush(void);
+/* Speculative pairing (csrc/gemv.cu): while one op/trans_op pair streams A, the two products of the pair that followed
+ * it last time are computed from the same staged tiles and parked; when that pair arrives it is served by the finalize
+ * step alone (one read of A fewer).  Any device write overlapping the speculated inputs drops the speculation, so results
+ * are bit-identical with it on or off.  tb_spec_stats: speculative passes launched / pairs served / speculations dropped. */
+int         tb_set_speculation(int on);
+int         tb_spec_stats(uint64_t* launched, uint64_t* served, uint64_t* dropped);
 /* diagnostics: host seconds spent waiting for host-visible scalars (and how many waits) since the last call; a host that
  * never waits is launch-bound, one that mostly waits is device-bound */
 int         tb_host_wait_stats(double* seconds, uint64_t* waits);

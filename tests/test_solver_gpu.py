@@ -405,3 +405,42 @@ def test_vector_programs_match_per_kernel_launches(name, dt):
     assert H.rel_linf(out[1][0], out[0][0]) <= tol and H.rel_linf(out[1][1], out[0][1]) <= tol
     for g, w in zip(out[1][2], out[0][2]):
         assert (not np.isfinite(w) and (g == w or np.isnan(w))) or abs(g - w) <= 50 * tol * max(abs(w), 1e-3)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_speculative_pairing_bit_identical_and_served(dt):
+    """csrc/gemv.cu "speculative pairing": with it on, the criteria_conv pair is served from products computed during the
+    previous pass over A (one read of A fewer per iteration) - iterates and residuals are bit-identical to the run with
+    it off, one pair per iteration is served in steady state, and the only dropped speculations are the learning ones."""
+    import ctypes as C
+    L = capi.lib()
+    blocks, n = SYN["stream"]()
+    m = sum(l for _, l in blocks)
+    a, b, c = H.make_instance(m, n, blocks, seed=9, dtype=dt)
+    abuf, av = H.device_matrix(a)
+    capi.check(L.tb_set_gemv_path(2))          # 2560 x 1024 through the streaming kernel
+    out = {}
+    iters = 30
+    try:
+        for on in (1, 0):
+            capi.check(L.tb_set_speculation(on))
+            st0 = [C.c_uint64() for _ in range(3)]
+            capi.check(L.tb_spec_stats(*[C.byref(v) for v in st0]))
+            s = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=True, fused_cone=True)
+            assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+            s.step(iters)
+            out[on] = s.xy() + ((s.last.c0, s.last.c1, s.last.c2),)
+            s.close()
+            st1 = [C.c_uint64() for _ in range(3)]
+            capi.check(L.tb_spec_stats(*[C.byref(v) for v in st1]))
+            launched, served, dropped = [b1.value - b0.value for b0, b1 in zip(st0, st1)]
+            if on:
+                assert served >= iters - 3 and launched >= served and dropped <= 4, (launched, served, dropped)
+            else:
+                assert launched == 0 and served == 0
+    finally:
+        capi.check(L.tb_set_speculation(1))
+        capi.check(L.tb_set_gemv_path(0))
+        abuf.release()
+    assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
+    assert out[1][2] == out[0][2]

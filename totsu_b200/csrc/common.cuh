@@ -179,6 +179,9 @@ struct Context {
     std::vector<Cmd> queue;
     bool pair_fusion = true;
     uint64_t pairs_fused = 0;
+    // speculative pairing (gemv.cu): the next pair's products computed in the current read of A
+    bool speculation = true;
+    uint64_t spec_launched = 0, spec_served = 0, spec_dropped = 0;
     // distributed
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
@@ -249,6 +252,10 @@ template <typename F> inline int api_defer(std::initializer_list<tb_view> reads,
     });
 }
 bool cmds_conflict(const Cmd& a, const Cmd& b);
+// speculative pairing hooks (gemv.cu): every range that changes on the device, every buffer that goes away
+void spec_note_write(tb_handle buf, size_t off, size_t len);
+void spec_note_release(tb_handle buf);
+void spec_reset();
 
 // ---- level-1 internals reused across translation units -------------------------------------------------
 template <typename T> void l1_scale(T alpha, T* x, size_t n);

@@ -97,6 +97,7 @@ char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite) {
     if (!b.host_newer.empty() && v.len > 0) {
         if (!(write && full_overwrite)) {
             b.host_newer.for_each_in(v.off, v.off + v.len, [&](size_t lo, size_t hi) {
+                spec_note_write(v.buf, lo, hi - lo);          // the device copy of [lo, hi) is about to change
                 size_t nb = (hi - lo) * b.esize;
                 if (nb <= Context::kSmallBytes) {
                     SmallPayload p;
@@ -110,6 +111,7 @@ char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite) {
         }
         b.host_newer.sub(v.off, v.off + v.len);
     }
+    if (write && v.len > 0) spec_note_write(v.buf, v.off, v.len);
     if (write && b.host && b.host_mut && v.len > 0) b.dev_newer.add(v.off, v.off + v.len);
     return b.dev + v.off * b.esize;
 }
@@ -324,6 +326,16 @@ int tb_flush(void) {
         vp_flush();
     });
 }
+int tb_set_speculation(int on) {
+    return api([&] {
+        require_init();
+        ctx().speculation = on != 0;
+        spec_reset();
+    });
+}
+int tb_spec_stats(uint64_t* launched, uint64_t* served, uint64_t* dropped) {
+    return api_raw([&] { *launched = ctx().spec_launched; *served = ctx().spec_served; *dropped = ctx().spec_dropped; });
+}
 int tb_host_wait_stats(double* seconds, uint64_t* waits) {
     return api_raw([&] {
         *seconds = ctx().box_wait_s; *waits = ctx().box_waits;
@@ -400,6 +412,7 @@ int tb_buf_release(tb_handle h) {
         Buffer& b = get_buf(h);
         Context& c = ctx();
         if (--b.refs > 0) return;                 // sub-slice wrappers of the binding are still alive
+        spec_note_release(h);
         if (c.last_lookup == h) c.last_lookup = 0;
         if (b.host && b.host_mut) host_sync_range(b, 0, b.len);
         if (b.small_slot >= 0) {
