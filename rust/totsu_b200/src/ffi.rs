@@ -67,6 +67,13 @@ extern "C" {
     pub fn tb_cone_destroy(cone: tb_handle) -> c_int;
     pub fn tb_cone_proj_f32(cone: tb_handle, dual_cone: c_int, x: tb_view, eps_zero: f32, psd_work: tb_view) -> c_int;
     pub fn tb_cone_group_min_f32(cone: tb_handle, dp_tau: tb_view) -> c_int;
+
+    // switches / housekeeping: none is needed for correctness - every call that returns data to the host drains deferred work
+    pub fn tb_flush() -> c_int;
+    pub fn tb_device_sync() -> c_int;
+    pub fn tb_set_pair_fusion(on: c_int) -> c_int;
+    pub fn tb_set_speculation(on: c_int) -> c_int;
+    pub fn tb_set_vprog(on: c_int) -> c_int;
 }
 
 /// The traits have no error channel, so a failed call panics - exactly like totsu_f32cuda asserts on every cuBLAS

@@ -104,22 +104,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t rank) {
-    uint32_t remote;
-    float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-    return v;
-}
-
 // shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute/arch/mma_sm100_desc.hpp SmemDescriptor layout):
 // start address >> 4 at [0,14), leading byte offset >> 4 at [16,30), stride byte offset >> 4 at [32,46), version 1 at [46,48)
 __host__ __device__ __forceinline__ uint64_t smem_desc_fields(uint32_t lbo, uint32_t sbo) {
