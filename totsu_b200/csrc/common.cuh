@@ -276,6 +276,9 @@ void dist_allgather_inplace(void* base, size_t count_per_rank, int dtype);   // 
 //   reduce: y[i] = alpha * sum_ranks sum_j part[j*ld+i] + beta*y[i], summed in rank order on every rank
 template <typename T> void dist_finalize_gather(const T* part, int nparts, size_t ld, size_t len_local, T alpha, T beta, T* y_base);
 template <typename T> void dist_finalize_reduce(const T* part, int nparts, size_t ld, size_t n, T alpha, T beta, T* y);
+template <typename T>
+void dist_finalize_pair(const T* part_n, int nparts_n, size_t ld_n, size_t len_local, T alpha_n, T beta_n, T* y_base,
+                        const T* part_t, int nparts_t, size_t ld_t, size_t n, T alpha_t, T beta_t, T* y_t);     // both in one exchange
 void dist_check_fault();      // throws if a peer-exchange wait timed out
 
 // ---- eig internals (cone.cu calls into eig.cu for PSD blocks) -------------------------------------------

@@ -176,6 +176,78 @@ __global__ void __launch_bounds__(256) peer_wait_kernel(const PeerPtrs pp, uint6
     }
 }
 
+// Both collectives of one op/trans_op pair in ONE exchange: the push kernel finalizes my slice of A x (alpha/beta applied,
+// stored into my y and every peer's stage) AND stores my partial of A^T x into every rank's stage behind the gather area
+// (stage layout: [world * len_g gathered slices | world * len_r reduce partials]), then releases one flag per peer; the
+// wait kernel acquires the flags once, copies the gathered slices and sums the reduce partials in rank order.  Halves the
+// launches and the flag round trips of a pair (6 exchanges per solver iteration -> 3).
+template <typename T>
+__global__ void __launch_bounds__(256) peer_push_pair_kernel(const PeerPtrs pp, uint64_t seq,
+                                                             const T* __restrict__ part_g, int nparts_g, size_t ld_g, size_t len_g, T alpha_g, T beta_g, T* y_local,
+                                                             const T* __restrict__ part_r, int nparts_r, size_t ld_r, size_t len_r, unsigned int* ticket) {
+    __shared__ bool last;
+    const size_t goff = (size_t)pp.rank * len_g;
+    const size_t rbase = (size_t)pp.world * len_g;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len_g + len_r; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < len_g) {
+            T s = T(0);
+            for (int j = 0; j < nparts_g; ++j) s += part_g[(size_t)j * ld_g + i];
+            T v = alpha_g * s;
+            if (beta_g != T(0)) v += beta_g * y_local[i];
+            y_local[i] = v;
+            for (int p = 0; p < pp.world; ++p)
+                if (p != pp.rank) stage_ptr<T>(pp, p, seq)[goff + i] = v;
+        } else {
+            const size_t k = i - len_g;
+            T s = T(0);
+            for (int j = 0; j < nparts_r; ++j) s += part_r[(size_t)j * ld_r + k];
+            for (int p = 0; p < pp.world; ++p) stage_ptr<T>(pp, p, seq)[rbase + (size_t)pp.rank * len_r + k] = s;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < pp.world) {
+        __threadfence_system();
+        const int p = threadIdx.x;
+        st_release_sys(reinterpret_cast<uint64_t*>(pp.region[p]) + pp.rank, seq);      // my own flag too: the reduce reads my partial from my stage
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) peer_wait_pair_kernel(const PeerPtrs pp, uint64_t seq, size_t len_g, T* y_g_base,
+                                                             size_t len_r, T alpha_r, T beta_r, T* y_r, int* fault) {
+    if (threadIdx.x < pp.world) {
+        const uint64_t* flag = reinterpret_cast<const uint64_t*>(pp.region[pp.rank]) + threadIdx.x;
+        if (ld_acquire_sys(flag) < seq) {
+            const unsigned long long t0 = global_ns();
+            while (ld_acquire_sys(flag) < seq) {
+                if (global_ns() - t0 > kSpinTimeoutNs) { *fault = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    const T* st = stage_ptr<T>(pp, pp.rank, seq);
+    const size_t total_g = len_g * (size_t)pp.world;
+    const size_t lo = len_g * (size_t)pp.rank, hi = lo + len_g;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_g + len_r; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < total_g) {
+            if (i < lo || i >= hi) y_g_base[i] = __ldcg(st + i);
+        } else {
+            const size_t k = i - total_g;
+            T s = T(0);
+            for (int r = 0; r < pp.world; ++r) s += __ldcg(st + total_g + (size_t)r * len_r + k);
+            T v = alpha_r * s;
+            if (beta_r != T(0)) v += beta_r * y_r[k];
+            y_r[k] = v;
+        }
+    }
+}
+
 static inline int px_grid(size_t len) {
     return (int)std::max<size_t>(1, std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 2));
 }
@@ -259,6 +331,27 @@ template <typename T> void dist_finalize_reduce(const T* part, int nparts, size_
     count_launch();
     l1_axpby<T>(alpha, tmp, beta, y, n);
 }
+// the two epilogues of a pair; one exchange when the peer path can take both (TB_P2P_PAIR=0 keeps them separate)
+template <typename T>
+void dist_finalize_pair(const T* part_n, int nparts_n, size_t ld_n, size_t len_local, T alpha_n, T beta_n, T* y_base,
+                        const T* part_t, int nparts_t, size_t ld_t, size_t n, T alpha_t, T beta_t, T* y_t) {
+    Context& c = ctx();
+    static const bool fused = [] { const char* e = getenv("TB_P2P_PAIR"); return !(e && e[0] == '0'); }();
+    if (fused && c.world > 1 && len_local > 0 && n > 0 && px_fits<T>((len_local + n) * (size_t)c.world)) {
+        const uint64_t seq = ++g_px.seq;
+        T* y_local = y_base + (size_t)c.rank * len_local;
+        peer_push_pair_kernel<T><<<px_grid(len_local + n), 256, 0, c.stream>>>(g_px.pp, seq, part_n, nparts_n, ld_n, len_local, alpha_n, beta_n, y_local,
+                                                                            part_t, nparts_t, ld_t, n, px_ticket());
+        TB_LAUNCH_CHECK();
+        peer_wait_pair_kernel<T><<<px_grid(len_local * c.world + n), 256, 0, c.stream>>>(g_px.pp, seq, len_local, y_base, n, alpha_t, beta_t, y_t, g_px.fault_dev);
+        TB_LAUNCH_CHECK();
+        return;
+    }
+    dist_finalize_gather<T>(part_n, nparts_n, ld_n, len_local, alpha_n, beta_n, y_base);
+    dist_finalize_reduce<T>(part_t, nparts_t, ld_t, n, alpha_t, beta_t, y_t);
+}
+template void dist_finalize_pair<float>(const float*, int, size_t, size_t, float, float, float*, const float*, int, size_t, size_t, float, float, float*);
+template void dist_finalize_pair<double>(const double*, int, size_t, size_t, double, double, double*, const double*, int, size_t, size_t, double, double, double*);
 template void dist_finalize_gather<float>(const float*, int, size_t, size_t, float, float, float*);
 template void dist_finalize_gather<double>(const double*, int, size_t, size_t, double, double, double*);
 template void dist_finalize_reduce<float>(const float*, int, size_t, size_t, float, float, float*);

@@ -538,6 +538,10 @@ static void stream_finalize_partials(const T* part_n, size_t n_splits, const T* 
                                      T alpha_n, T beta_n, T* y_n, T alpha_t, T beta_t, T* y_t, bool sharded) {
     const bool do_n = y_n != nullptr, do_t = y_t != nullptr;
     if (sharded) {
+        if (do_n && do_t) {
+            dist_finalize_pair<T>(part_n, (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n, part_t, (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
+            return;
+        }
         if (do_n) dist_finalize_gather<T>(part_n, (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n);
         if (do_t) dist_finalize_reduce<T>(part_t, (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t);
         return;
