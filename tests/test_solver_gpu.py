@@ -370,15 +370,18 @@ def test_front_end_qp_matches_fused_dense(dt):
     s1.close(); s2.close(); abuf.release()
 
 
+WIDE = {"wide": (lambda: ([(SOC, 64)] * 512 + [(RPOS, 20000)], 600))}      # vectors of 106K elements: "wide" (barrier-free) programs
+
+
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("name", ["socp", "qp_like", "stream"])
+@pytest.mark.parametrize("name", ["socp", "qp_like", "stream", "wide"])
 def test_vector_programs_match_per_kernel_launches(name, dt):
     """csrc/vprog.cu: recording the small vector commands into one launch per batch changes neither the order of
     operations nor (beyond the double-precision accumulation of the dot products) the arithmetic: 40 iterations with
     tb_set_vprog(1) and tb_set_vprog(0) agree to rounding, and the batched run really batches (>= 2 micro-ops per launch incl. set-up)."""
     import ctypes as C
     L = capi.lib()
-    blocks, n = SYN[name]()
+    blocks, n = (SYN[name] if name in SYN else WIDE[name])()
     m = sum(l for _, l in blocks)
     a, b, c = H.make_instance(m, n, blocks, seed=5, dtype=dt)
     abuf, av = H.device_matrix(a)

@@ -136,7 +136,7 @@ struct Context {
     int sm_count = 148;
     StreamRef stream;
     bool vprog = true;                   // record small vector kernels into one launch (vprog.cu); tb_set_vprog
-    uint64_t vprog_launches = 0, vprog_ops = 0;
+    uint64_t vprog_launches = 0, vprog_ops = 0, vprog_wide_launches = 0;
     std::vector<Buffer> bufs;            // handle = index + 1
     std::vector<int64_t> free_ids;
     // scratch for two-stage (deterministic) reductions / matvec partials

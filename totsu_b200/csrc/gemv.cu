@@ -43,7 +43,7 @@ __global__ void finalize_kernel(const T* __restrict__ part, int nparts, size_t l
 
 template <typename T> void l2_finalize(const T* part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
     if (len == 0) return;
-    if (vp_enabled(len)) { vp_finalize(DT<T>::id, part, nparts, ld, len, (double)alpha, (double)beta, y); return; }
+    if (vp_enabled_wide(len)) { vp_finalize(DT<T>::id, part, nparts, ld, len, (double)alpha, (double)beta, y); return; }
     int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
     finalize_kernel<T><<<g, 256, 0, ctx().stream>>>(part, nparts, ld, len, alpha, beta, y);
     TB_LAUNCH_CHECK();
@@ -78,7 +78,7 @@ static void finalize2(const T* part_a, int nparts_a, size_t ld_a, size_t len_a, 
                       const T* part_b, int nparts_b, size_t ld_b, size_t len_b, T alpha_b, T beta_b, T* y_b) {
     const size_t len = len_a + len_b;
     if (len == 0) return;
-    if (vp_enabled(std::max(len_a, len_b))) {     // two independent micro-ops: no barrier between them
+    if (vp_enabled_wide(std::max(len_a, len_b))) {     // two independent micro-ops: no barrier between them
         if (len_a) vp_finalize(DT<T>::id, part_a, nparts_a, ld_a, len_a, (double)alpha_a, (double)beta_a, y_a);
         if (len_b) vp_finalize(DT<T>::id, part_b, nparts_b, ld_b, len_b, (double)alpha_b, (double)beta_b, y_b);
         return;
@@ -207,7 +207,7 @@ template <typename T, bool ABS>
 static void run_generic_n(const T* A, size_t lda, size_t n_row, size_t n_col, const T* x, T alpha, T beta, T* y) {
     Context& c = ctx();
     if (n_row == 0) return;
-    if (!ABS && n_col == 1 && vp_enabled(n_row)) {       // an n x 1 operator applied to a device scalar: y = alpha * A * x[0] + beta * y
+    if (!ABS && n_col == 1 && vp_enabled_wide(n_row)) {       // an n x 1 operator applied to a device scalar: y = alpha * A * x[0] + beta * y
         vp_axs(DT<T>::id, (double)alpha, A, x, (double)beta, y, n_row);
         return;
     }

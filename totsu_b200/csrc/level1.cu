@@ -108,7 +108,7 @@ template <typename T, int MODE> static double reduce_sync(const T* x, size_t cou
 
 template <typename T> void l1_scale(T alpha, T* x, size_t n) {
     if (n == 0) return;
-    if (vp_enabled(n)) {
+    if (vp_enabled_wide(n)) {
         if (alpha == T(0)) vp_fill(DT<T>::id, x, 0.0, n);
         else vp_scale(DT<T>::id, (double)alpha, x, n);
         return;
@@ -120,13 +120,13 @@ template <typename T> void l1_scale(T alpha, T* x, size_t n) {
 }
 template <typename T> void l1_copy(const T* x, T* y, size_t n) {
     if (n == 0) return;
-    if (vp_enabled(n)) { vp_copy(DT<T>::id, x, y, n); return; }
+    if (vp_enabled_wide(n)) { vp_copy(DT<T>::id, x, y, n); return; }
     copy_kernel<T><<<grid_for(n), kThreads, 0, ctx().stream>>>(x, y, n);
     TB_LAUNCH_CHECK();
 }
 template <typename T> void l1_axpby(T alpha, const T* x, T beta, T* y, size_t n) {
     if (n == 0) return;
-    if (vp_enabled(n)) { vp_axpby(DT<T>::id, (double)alpha, x, (double)beta, y, n); return; }
+    if (vp_enabled_wide(n)) { vp_axpby(DT<T>::id, (double)alpha, x, (double)beta, y, n); return; }
     Context& c = ctx();
     int g = grid_for(n);
     if (beta == T(0)) axpby_kernel<T, 0><<<g, kThreads, 0, c.stream>>>(alpha, x, beta, y, n);
@@ -185,7 +185,7 @@ template <typename T> static void api_adds(T s, tb_view y) {
     require_init();
     T* py = wptr<T>(y);
     if (y.len == 0) return;
-    if (vp_enabled(y.len)) { vp_adds(DT<T>::id, (double)s, py, y.len); return; }
+    if (vp_enabled_wide(y.len)) { vp_adds(DT<T>::id, (double)s, py, y.len); return; }
     adds_kernel<T><<<grid_for(y.len), kThreads, 0, ctx().stream>>>(s, py, y.len);
     TB_LAUNCH_CHECK();
 }
@@ -204,7 +204,7 @@ template <typename T> static void api_transform_di(T alpha, tb_view mat, tb_view
     T* py = wptr<T>(y, beta == T(0));
     size_t n = y.len;
     if (n == 0) return;
-    if (vp_enabled(n)) { vp_diag(DT<T>::id, (double)alpha, pd, px, (double)beta, py, n); return; }
+    if (vp_enabled_wide(n)) { vp_diag(DT<T>::id, (double)alpha, pd, px, (double)beta, py, n); return; }
     Context& c = ctx();
     int g = grid_for(n);
     if (beta == T(0)) diag_kernel<T, 0><<<g, kThreads, 0, c.stream>>>(alpha, pd, px, beta, py, n);

@@ -16,9 +16,12 @@
 // have produced them in this launch.  Reductions (dot products, norms) are two micro-ops: per-CTA partials in double to
 // a small global slot, barrier, then a fixed-order sum of the 8 partials - deterministic, no atomics.
 //
-// Only vectors of <= 48K elements are recorded (vp_enabled(n)): 8 SMs cannot move longer ones faster than a full-grid
-// kernel, and a software grid barrier across all SMs measured no cheaper than a launch boundary (~3 us in a dependent
-// chain; profiles/r01_vprog_summary.md), so longer vectors keep their own kernels.  Measured: small SOCP (vectors of
+// Programs whose vectors are all <= 48K elements run on the cluster.  8 SMs cannot move longer vectors faster than a
+// full-grid kernel, and a software grid barrier across all SMs measured no cheaper than a launch boundary (~3 us in a
+// dependent chain; profiles/r01_vprog_summary.md) - so a program that contains a longer vector is "wide": it runs as an
+// ordinary grid of up to two CTAs per SM, holds no barrier at all (the recorder cuts it at every hazard instead) and
+// no reductions; what it still saves is one launch per run of independent or same-thread-dependent element-wise ops
+// (finalize + the c / b vector-operator updates + axpby chains of SelfDualEmbed::op / trans_op).  Measured: small SOCP (vectors of
 // 20K) 0.276 -> 0.223 ms per iteration, C2 (43K) 0.498 -> 0.483 ms; C3 (147K) unchanged by construction.
 #include "common.cuh"
 #include "vprog.cuh"
@@ -33,6 +36,7 @@ constexpr int VP_MAX_OPS = 44;
 constexpr int VP_SLOTS = 32;            // reduction slots of VP_MAX_CTAS doubles each
 constexpr int VP_MAX_CTAS = VP_CLUSTER;
 constexpr size_t VP_MAX_N = 49152;      // longest vector worth running on one cluster of 8 SMs
+constexpr size_t VP_WIDE_MAX_N = size_t(1) << 22;    // beyond this a dedicated kernel with a larger grid is the better tool
 
 enum : uint8_t {
     VOP_FILL = 1,        // y[i] = a
@@ -162,15 +166,18 @@ __device__ __forceinline__ double combine_slot(const double* slot, int g) {
     return tbd::warp_sum(s);
 }
 
-__global__ void __cluster_dims__(VP_CLUSTER, 1, 1) __launch_bounds__(VP_THREADS, 1) vprog_kernel(const __grid_constant__ Program prog) {
+// CLUSTER: one cluster of VP_CLUSTER CTAs with hardware barriers.  Otherwise ("wide" programs: some vector is longer than
+// VP_MAX_N) an ordinary grid of up to two CTAs per SM and NO barriers: the recorder cuts a wide program at every hazard.
+template <bool CLUSTER>
+__device__ __forceinline__ void run_program(const Program& prog) {
     __shared__ double red[32];
-    const unsigned rank = cluster_ctarank();
-    constexpr int g = VP_CLUSTER;
+    const unsigned rank = CLUSTER ? cluster_ctarank() : blockIdx.x;
+    const int g = CLUSTER ? VP_CLUSTER : (int)gridDim.x;
     const size_t gtid = (size_t)rank * VP_THREADS + threadIdx.x;
     const size_t gstride = (size_t)g * VP_THREADS;
     for (int k = 0; k < prog.n_ops; ++k) {
         const MicroOp& op = prog.ops[k];
-        if (op.barrier) cluster_barrier();
+        if (CLUSTER && op.barrier) cluster_barrier();
         switch (op.code) {
             case VOP_PART_DOT:
             case VOP_PART_SUMSQ:
@@ -224,6 +231,13 @@ __global__ void __cluster_dims__(VP_CLUSTER, 1, 1) __launch_bounds__(VP_THREADS,
     }
 }
 
+__global__ void __cluster_dims__(VP_CLUSTER, 1, 1) __launch_bounds__(VP_THREADS, 1) vprog_kernel(const __grid_constant__ Program prog) {
+    run_program<true>(prog);
+}
+__global__ void __launch_bounds__(VP_THREADS, 2) vprog_wide_kernel(const __grid_constant__ Program prog) {
+    run_program<false>(prog);
+}
+
 // ---- recorder ------------------------------------------------------------------------------------------
 // tag: the op touches element i of this range from the thread that owns index i (identity mapping from `lo`); two such
 // accesses with the same base are ordered by program order inside one thread and need no barrier
@@ -235,6 +249,9 @@ struct Recorder {
     int next_slot = 0;
     double* slots = nullptr;
     bool flushing = false;
+    bool wide = false;            // some op is longer than VP_MAX_N: barrier-free, runs on the whole GPU
+    bool has_barrier = false, has_reduction = false;
+    size_t max_n = 0;
 };
 Recorder g_rec;
 
@@ -249,14 +266,25 @@ inline Range range_of(const void* p, size_t bytes) { return Range{reinterpret_ca
 inline Range elems_of(const void* p, size_t bytes) { return Range{reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes, true}; }
 
 // Append one micro-op; rd[] / wr[] are the byte ranges it reads / writes.
-void push(MicroOp op, std::initializer_list<Range> rd, std::initializer_list<Range> wr) {
+void push(MicroOp op, std::initializer_list<Range> rd, std::initializer_list<Range> wr, bool reduction = false) {
     Recorder& R = g_rec;
     if (R.prog.n_ops == VP_MAX_OPS) vp_flush();
+    const bool big = (size_t)op.n > VP_MAX_N;
+    if (R.prog.n_ops > 0) {
+        // a wide program has neither barriers nor reductions (their partial slots are sized for the cluster)
+        if (big && !R.wide && (R.has_barrier || R.has_reduction)) vp_flush();
+        if (reduction && R.wide) vp_flush();
+    }
     bool hazard = false;
     for (const Range& r : rd) hazard = hazard || overlaps(R.writes, r);
     for (const Range& w : wr) hazard = hazard || overlaps(R.writes, w) || overlaps(R.reads, w);
+    if (hazard && R.prog.n_ops > 0 && (R.wide || big)) { vp_flush(); hazard = false; }      // cut instead of a barrier
     if (hazard) { R.reads.clear(); R.writes.clear(); }
     op.barrier = (hazard && R.prog.n_ops > 0) ? 1 : 0;
+    if (big) R.wide = true;
+    if (op.barrier) R.has_barrier = true;
+    if (reduction) R.has_reduction = true;
+    R.max_n = std::max<size_t>(R.max_n, (size_t)op.n);
     for (const Range& r : rd) if (r.lo < r.hi) R.reads.push_back(r);
     for (const Range& w : wr) if (w.lo < w.hi) R.writes.push_back(w);
     R.prog.ops[R.prog.n_ops++] = op;
@@ -272,6 +300,8 @@ Range slot_range(int slot) { return range_of(g_rec.slots + (size_t)slot * VP_MAX
 }  // namespace
 
 bool vp_enabled(size_t n) { return ctx().vprog && n <= VP_MAX_N; }
+// element-wise ops of any practical length can be recorded: beyond VP_MAX_N the program becomes a barrier-free "wide" one
+bool vp_enabled_wide(size_t n) { return ctx().vprog && n <= VP_WIDE_MAX_N; }
 
 void vp_flush() {
     Recorder& R = g_rec;
@@ -280,10 +310,17 @@ void vp_flush() {
     Context& c = ctx();
     R.prog.slots = R.slots;
     R.prog.box = c.hostbox_dev;
-    vprog_kernel<<<VP_CLUSTER, VP_THREADS, 0, c.stream.raw>>>(R.prog);
+    if (R.wide) {
+        const int g = (int)std::max<size_t>(1, std::min<size_t>((R.max_n + VP_THREADS - 1) / VP_THREADS, (size_t)c.sm_count * 2));
+        vprog_wide_kernel<<<g, VP_THREADS, 0, c.stream.raw>>>(R.prog);
+        c.vprog_wide_launches += 1;
+    } else {
+        vprog_kernel<<<VP_CLUSTER, VP_THREADS, 0, c.stream.raw>>>(R.prog);
+    }
     const cudaError_t e = cudaGetLastError();
     R.prog.n_ops = 0;
     R.next_slot = 0;
+    R.wide = false; R.has_barrier = false; R.has_reduction = false; R.max_n = 0;
     R.reads.clear();
     R.writes.clear();
     R.flushing = false;
@@ -364,19 +401,19 @@ void vp_set1(int dtype, void* y, double v) {
 void vp_dot(int dtype, double a, const void* x, const void* d, size_t n, double b, void* y) {
     const int slot = take_slot();
     MicroOp p = mk(VOP_PART_DOT, dtype); p.x = x; p.p2 = d; p.n = n; p.aux = (uint32_t)slot;
-    push(p, {range_of(x, n * es(dtype)), range_of(d, n * es(dtype))}, {slot_range(slot)});
+    push(p, {range_of(x, n * es(dtype)), range_of(d, n * es(dtype))}, {slot_range(slot)}, true);
     MicroOp q = mk(VOP_COMBINE_Y, dtype); q.y = y; q.a = a; q.b = b; q.aux = (uint32_t)slot; q.mode = b == 0.0 ? 0 : 2;
-    if (q.mode == 0) push(q, {slot_range(slot)}, {range_of(y, es(dtype))});
-    else push(q, {slot_range(slot), range_of(y, es(dtype))}, {range_of(y, es(dtype))});
+    if (q.mode == 0) push(q, {slot_range(slot)}, {range_of(y, es(dtype))}, true);
+    else push(q, {slot_range(slot), range_of(y, es(dtype))}, {range_of(y, es(dtype))}, true);
 }
 // sum of squares (mode 0) or of absolute values (mode 1) of x[i * inc], i < count, delivered to the host
 double vp_reduce_to_host(int dtype, int mode, const void* x, size_t count, size_t inc) {
     const int slot = take_slot();
     MicroOp p = mk(mode == 0 ? VOP_PART_SUMSQ : VOP_PART_ABSSUM, dtype); p.x = x; p.n = count; p.aux = (uint32_t)slot; p.aux2 = inc;
-    push(p, {range_of(x, ((count - 1) * inc + 1) * es(dtype))}, {slot_range(slot)});
+    push(p, {range_of(x, ((count - 1) * inc + 1) * es(dtype))}, {slot_range(slot)}, true);
     const uint64_t seq = box_next();
     MicroOp q = mk(VOP_COMBINE_BOX, dtype); q.aux = (uint32_t)slot; q.aux2 = seq;
-    push(q, {slot_range(slot)}, {});
+    push(q, {slot_range(slot)}, {}, true);
     vp_flush();
     return box_wait(seq);
 }
