@@ -301,3 +301,51 @@ def test_proj_psd_tensor_core_paths_vs_oracle(k, path, request):
     capi.check(capi.fn("tb_proj_psd", np.float32)(xb.view(), 1e-12, wb.view()))
     xb.release(); wb.release()
     assert np.abs(x - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (k, path)
+
+
+@pytest.mark.parametrize("k", [64, 132])
+def test_cone_proj_pairing_batches_the_two_psd_projections(k):
+    """The solver's two projections per iteration (dual cone on y, primal cone on s: solver.rs:548-549) on a product cone
+    with a PSD block: the first tb_cone_proj_f32 is parked, the second runs both as one batch (tb_psd_pairs counts it);
+    results match the oracle and the unbatched run, and a lone projection still completes when anything else is called."""
+    import ctypes as C
+    L = capi.lib()
+    sk = k * (k + 1) // 2
+    blocks = [(RPOS, 5), (PSD, sk), (SOC, 7)]
+    m = sum(l for _, l in blocks)
+    rng = np.random.default_rng(k)
+
+    def vec():
+        g = rng.standard_normal((k, k))
+        return np.concatenate([rng.standard_normal(5), svec((g + g.T) / 2), rng.standard_normal(7)]).astype(np.float32)
+    y0, s0 = vec(), vec()
+    want = []
+    for v, dual in ((y0, True), (s0, False)):
+        w = v.astype(np.float64).copy()
+        oracle_cone(blocks).proj(dual, w)
+        want.append(w)
+    h = _cone(blocks)
+    res = {}
+    for pairing in (1, 0):
+        capi.check(L.tb_set_psd_pairing(pairing))
+        n0 = C.c_uint64(); capi.check(L.tb_psd_pairs(C.byref(n0)))
+        buf = np.concatenate([y0, s0]).copy()
+        vb, wb = capi.Buf(buf), capi.Buf(np.zeros(2 * k * k + k, dtype=np.float32))
+        capi.check(L.tb_cone_proj_f32(h, 1, vb.view(0, m), 1e-12, wb.view()))
+        capi.check(L.tb_cone_proj_f32(h, 0, vb.view(m, m), 1e-12, wb.view()))
+        vb.release(); wb.release()
+        n1 = C.c_uint64(); capi.check(L.tb_psd_pairs(C.byref(n1)))
+        assert n1.value - n0.value == (1 if pairing else 0)
+        res[pairing] = buf
+        for i in range(2):
+            got = buf[i * m:(i + 1) * m]
+            assert np.abs(got - want[i]).max() <= 2e-5 * max(1.0, np.abs(want[i]).max()), (pairing, i)
+    assert np.abs(res[1] - res[0]).max() <= 2e-5 * np.abs(res[0]).max()
+    # a single parked projection is flushed by the next call (here: the release of its buffer)
+    capi.check(L.tb_set_psd_pairing(1))
+    lone = y0.copy()
+    vb, wb = capi.Buf(lone), capi.Buf(np.zeros(2 * k * k + k, dtype=np.float32))
+    capi.check(L.tb_cone_proj_f32(h, 1, vb.view(), 1e-12, wb.view()))
+    vb.release(); wb.release()
+    assert np.abs(lone - want[0]).max() <= 2e-5 * max(1.0, np.abs(want[0]).max())
+    capi.check(L.tb_cone_destroy(h))

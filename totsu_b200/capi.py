@@ -55,6 +55,7 @@ def _signatures():
         "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_psd_path": (i, [i]),
         "tb_set_pair_fusion": (i, [i]), "tb_pairs_fused": (i, [C.POINTER(u64)]),
         "tb_host_wait_stats": (i, [C.POINTER(C.c_double), C.POINTER(u64)]),
+        "tb_set_psd_pairing": (i, [i]), "tb_psd_pairs": (i, [C.POINTER(u64)]),
         "tb_set_speculation": (i, [i]), "tb_spec_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "tb_set_vprog": (i, [i]), "tb_vprog_stats": (i, [C.POINTER(u64), C.POINTER(u64)]), "tb_flush": (i, []),
         "tb_prof_enable": (i, [i]), "tb_prof_read": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

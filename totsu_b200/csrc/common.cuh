@@ -163,6 +163,8 @@ struct Context {
     uint64_t buf_gen = 0;
     tb_handle last_lookup = 0;
     int gemv_mode = 0;
+    bool psd_pairing = true;             // park the first ConePSD projection of an iteration and batch it with the second (cone.cu)
+    uint64_t psd_pairs = 0;
     int psd_mode = 0;                    // 0: matrix-sign iteration (tcgen05 GEMMs for f32), 1: Jacobi eigendecomposition, 2: sign on FP32/FP64 pipes, 3: tcgen05 without split-K
     char* eig_scratch = nullptr;         // 3 k*k matrices for the sign iteration
     size_t eig_scratch_bytes = 0;
@@ -215,9 +217,27 @@ inline void count_launch(int n = 1) { ctx().launches += (uint64_t)n; }
         ::tb::count_launch();               \
     } while (0)
 
+// A parked cone projection (cone.cu: the first of the two projections of an iteration waits for its partner) runs before
+// anything else touches the library.
+extern bool g_cone_pending;
+void cone_flush_pending();
+
 // API wrapper: translate internal exceptions to status codes.
+template <typename F> inline int api_keep_pending(F f) {
+    try {
+        f();
+        return TB_OK;
+    } catch (const Error& e) {
+        ctx().last_error = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        ctx().last_error = e.what();
+        return TB_ERR_STATE;
+    }
+}
 template <typename F> inline int api_raw(F f) {
     try {
+        if (g_cone_pending) cone_flush_pending();
         f();
         return TB_OK;
     } catch (const Error& e) {
@@ -283,8 +303,12 @@ void dist_check_fault();      // throws if a peer-exchange wait timed out
 
 // ---- eig internals (cone.cu calls into eig.cu for PSD blocks) -------------------------------------------
 template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len);
+bool psd_pair_usable(size_t sn, const float* work);
+void psd_project_pair(float* x0, float* x1, size_t sn, float* work, size_t work_len);     // two projections, every GEMM step one batched launch
 // tcgen05 3xTF32 symmetric GEMM (psd_tc.cu): C = alpha*A*B + beta*D + gamma*I, all symmetric k x k column-major f32
 bool symm_gemm_tc_usable(const float* A, const float* B, const float* D, const float* C, size_t k);
+void symm_gemm_tc_pair(const float* const A[2], const float* const B[2], const float* const D[2], float* const C[2], size_t k,
+                       float alpha, float beta, float gamma, int splitk);   // two independent products, one launch
 void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk,
                   unsigned long long* trace = nullptr);   // trace: 16 device u64 phase stamps of CTA 0 (diagnostics)
 

@@ -201,6 +201,83 @@ template <typename T> static void cone_proj(tb_handle h, int dual_cone, tb_view 
     }
 }
 
+// ---- pairing of the two projections of one iteration ----------------------------------------------------------
+// The solver projects the y block onto K* and the s block onto K back to back (solver.rs:548-549).  For a cone with PSD
+// blocks in f32 the first call is parked; when the second arrives (same cone, disjoint vector, same work buffer) the PSD
+// blocks of both run as ONE batch on the tensor cores (eig.cu:psd_project_pair).  Any other API call runs the parked
+// projection first (api_raw checks g_cone_pending), so program order is preserved.
+struct PendingProj {
+    tb_handle h = 0;
+    int dual = 0;
+    tb_view x{0, 0, 0}, w{0, 0, 0};
+    float eps = 0.f;
+};
+static PendingProj g_pending;
+bool g_cone_pending = false;
+
+void cone_flush_pending() {
+    if (!g_cone_pending) return;
+    g_cone_pending = false;
+    const PendingProj p = g_pending;
+    cone_proj<float>(p.h, p.dual, p.x, p.eps, p.w);
+}
+
+static bool views_disjoint(const tb_view& a, const tb_view& b) {
+    return a.buf != b.buf || a.off + a.len <= b.off || b.off + b.len <= a.off;
+}
+
+// both projections at once: non-PSD blocks through cone_kernel per vector, PSD blocks pairwise batched
+static void cone_proj_pair(const PendingProj& p0, tb_handle h, int dual1, tb_view x1, float eps1, tb_view w) {
+    ConeSet& cs = get_cone(h);
+    Context& c = ctx();
+    float* px0 = wptr<float>(p0.x);
+    float* px1 = wptr<float>(x1);
+    float* pw = wptr<float>(w);
+    if (cs.has_work) {
+        cone_kernel<float, 0><<<cs.n_items, CN_THREADS, 0, c.stream>>>(px0, cs.d_items, cs.d_small, p0.dual);
+        TB_LAUNCH_CHECK();
+        cone_kernel<float, 0><<<cs.n_items, CN_THREADS, 0, c.stream>>>(px1, cs.d_items, cs.d_small, dual1);
+        TB_LAUNCH_CHECK();
+    }
+    size_t off = 0;
+    for (const tb_cone_block& b : cs.blocks) {
+        if (b.type == TB_CONE_PSD && b.len > 0) {
+            if (psd_pair_usable((size_t)b.len, pw) && ((reinterpret_cast<uintptr_t>(px0 + off) | reinterpret_cast<uintptr_t>(px1 + off)) & 3u) == 0) {
+                psd_project_pair(px0 + off, px1 + off, (size_t)b.len, pw, w.len);
+                c.psd_pairs += 1;
+            } else {
+                psd_project<float>(px0 + off, (size_t)b.len, p0.eps, pw, w.len);
+                psd_project<float>(px1 + off, (size_t)b.len, eps1, pw, w.len);
+            }
+        }
+        off += (size_t)b.len;
+    }
+}
+
+static void cone_proj_submit_f32(tb_handle h, int dual, tb_view x, float eps, tb_view w) {
+    require_init();
+    if (!ctx().queue.empty()) queue_drain();
+    ConeSet& cs = get_cone(h);
+    TB_REQUIRE(x.len == cs.total_len, "cone proj: vector length != sum of block lengths");
+    if (g_cone_pending) {
+        const PendingProj p0 = g_pending;
+        const bool pairable = p0.h == h && views_disjoint(p0.x, x) && p0.w.buf == w.buf && p0.w.off == w.off && p0.w.len == w.len &&
+                              views_disjoint(p0.x, w) && views_disjoint(x, w);
+        g_cone_pending = false;
+        if (pairable) {
+            cone_proj_pair(p0, h, dual, x, eps, w);
+            return;
+        }
+        cone_proj<float>(p0.h, p0.dual, p0.x, p0.eps, p0.w);
+    }
+    if (cs.has_psd && ctx().psd_mode == 0 && ctx().psd_pairing) {
+        g_pending.h = h; g_pending.dual = dual; g_pending.x = x; g_pending.w = w; g_pending.eps = eps;
+        g_cone_pending = true;                 // parked: runs with its partner, or alone as soon as anything else is called
+        return;
+    }
+    cone_proj<float>(h, dual, x, eps, w);
+}
+
 template <typename T> static void cone_group_min(tb_handle h, tb_view dp_tau) {
     require_init();
     ConeSet& cs = get_cone(h);
@@ -265,7 +342,13 @@ int tb_cone_destroy(tb_handle h) {
         ctx().cones[(size_t)h - 1] = nullptr;
     });
 }
-int tb_cone_proj_f32(tb_handle cone, int dual, tb_view x, float eps, tb_view w) { return api([&] { cone_proj<float>(cone, dual, x, eps, w); }); }
+int tb_cone_proj_f32(tb_handle cone, int dual, tb_view x, float eps, tb_view w) { return api_keep_pending([&] { cone_proj_submit_f32(cone, dual, x, eps, w); }); }
+int tb_set_psd_pairing(int on) {
+    return api([&] { ctx().psd_pairing = on != 0; });
+}
+int tb_psd_pairs(uint64_t* out) {
+    return api_raw([&] { *out = ctx().psd_pairs; });
+}
 int tb_cone_proj_f64(tb_handle cone, int dual, tb_view x, double eps, tb_view w) { return api([&] { cone_proj<double>(cone, dual, x, eps, w); }); }
 int tb_cone_group_min_f32(tb_handle cone, tb_view t) { return api([&] { cone_group_min<float>(cone, t); }); }
 int tb_cone_group_min_f64(tb_handle cone, tb_view t) { return api([&] { cone_group_min<double>(cone, t); }); }

@@ -401,6 +401,59 @@ template <typename T> static void psd_project_sign(T* x, size_t k, T* work) {
     TB_LAUNCH_CHECK();
 }
 
+// Both ConePSD projections of one solver iteration (dual cone on y, primal cone on s: solver.rs:548-549) as one batch:
+// every step of the sign iteration is ONE launch of the tcgen05 GEMM over both problems (blockIdx.y), which fills
+// twice as many SMs.  Problem 0 uses the caller's work buffer like psd_project_sign, problem 1 lives in the library's
+// scratch.  f32, k >= 64, k % 4 == 0, 16-byte aligned views (psd_pair_usable).
+bool psd_pair_usable(size_t sn, const float* work) {
+    const size_t k = tri_dim(sn);
+    return ctx().psd_mode == 0 && k * (k + 1) / 2 == sn && k >= 64 && k % 4 == 0 && (reinterpret_cast<uintptr_t>(work) & 15u) == 0;
+}
+
+void psd_project_pair(float* x0, float* x1, size_t sn, float* work, size_t work_len) {
+    Context& c = ctx();
+    const size_t k = tri_dim(sn), kk = k * k;
+    TB_REQUIRE(work_len >= 2 * kk + k, "ConePSD: work shortage");
+    float* sc = reinterpret_cast<float*>(eig_scratch((8 * kk + k) * sizeof(float)));
+    float* X[2] = {work, sc + 3 * kk};
+    float* S0[2] = {work + kk + k, sc + 3 * kk + kk + k};
+    float* S1[2] = {sc, sc + 5 * kk + k};
+    float* T2[2] = {sc + kk, sc + 6 * kk + k};
+    float* P[2] = {sc + 2 * kk, sc + 7 * kk + k};
+    float* xs[2] = {x0, x1};
+    const float sq2 = 1.41421356237309504880f;
+    const unsigned gkk = (unsigned)((kk + 255) / 256);
+    for (int i = 0; i < 2; ++i) {
+        double* sumsq = c.mailbox_dev + 16 + i;
+        unpack_kernel<float><<<gkk, 256, 0, c.stream>>>(xs[i], k, 1, sq2, X[i]);
+        TB_LAUNCH_CHECK();
+        l1_sumsq_async<float>(X[i], kk, sumsq);
+        scale_inv_norm_kernel<float><<<std::min<unsigned>(gkk, 4096u), 256, 0, c.stream>>>(X[i], S0[i], kk, sumsq);
+        TB_LAUNCH_CHECK();
+    }
+    const int n1 = 10, n2 = 8;                                  // same schedule as psd_project_sign<float>
+    const float qa = 3.4445f, qb = -4.7750f, qc = 2.0315f;
+    const float* nul[2] = {nullptr, nullptr};
+    float* S[2] = {S0[0], S0[1]};
+    float* Sn[2] = {S1[0], S1[1]};
+    for (int it = 0; it < n1; ++it) {
+        symm_gemm_tc_pair(S, S, nul, T2, k, 1.f, 0.f, 0.f, 0);             // T2 = S^2
+        symm_gemm_tc_pair(T2, T2, T2, P, k, qc, qb, qa, 0);               // P = c S^4 + b S^2 + a I
+        symm_gemm_tc_pair(S, P, nul, Sn, k, 1.f, 0.f, 0.f, 0);            // S' = S P
+        std::swap(S[0], Sn[0]); std::swap(S[1], Sn[1]);
+    }
+    for (int it = 0; it < n2; ++it) {
+        symm_gemm_tc_pair(S, S, nul, P, k, -0.5f, 0.f, 1.5f, 0);          // P = 1.5 I - 0.5 S^2
+        symm_gemm_tc_pair(S, P, nul, Sn, k, 1.f, 0.f, 0.f, 0);            // S' = S P
+        std::swap(S[0], Sn[0]); std::swap(S[1], Sn[1]);
+    }
+    symm_gemm_tc_pair(X, S, X, P, k, 0.5f, 0.5f, 0.f, 0);                 // proj = (X S + X) / 2
+    for (int i = 0; i < 2; ++i) {
+        pack_kernel<float><<<gkk, 256, 0, c.stream>>>(P[i], k, 1, 1.f / sq2, xs[i]);
+        TB_LAUNCH_CHECK();
+    }
+}
+
 template <typename T> void psd_project(T* x, size_t sn, T eps_zero, T* work, size_t work_len) {
     (void)eps_zero;
     const size_t k = tri_dim(sn);

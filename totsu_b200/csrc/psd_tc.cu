@@ -149,7 +149,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
     return t;
 }
 // phase stamps of CTA 0 (diagnostics: tb_symm_gemm_trace); slot i of `trace` is written by one thread
-#define TC_STAMP(i) do { if (trace != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && (tid == 0)) trace[i] = gtimer(); } while (0)
+#define TC_STAMP(i) do { if (trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid == 0)) trace[i] = gtimer(); } while (0)
 
 template <int SPLITK> struct Cfg {
     static constexpr int STAGES = SPLITK > 1 ? 2 : 3;             // + one chunk in flight in registers
@@ -160,12 +160,24 @@ template <int SPLITK> struct Cfg {
     static_assert(ROWS * PAD * 4 <= PIPE_BYTES, "the mirror staging tile reuses the pipeline buffers");
 };
 
+// Up to two independent products per launch (blockIdx.y): the two ConePSD projections of one solver iteration (dual cone
+// on the y block, primal cone on the s block: solver.rs:548-549) run as one batch and fill twice as many SMs.
+struct TcOperands {
+    const float* A[2];
+    const float* B[2];
+    const float* D[2];
+    float* C[2];
+};
+
 // C = alpha * (A * B) + beta * D + gamma * I; A, B, D symmetric k x k column-major, k % 4 == 0, 16-byte aligned.
-// grid = (upper tile pairs, 1, SPLITK), cluster (1, 1, SPLITK).
+// grid = (upper tile pairs, batch, SPLITK), cluster (1, 1, SPLITK).
 template <int SPLITK>
-__global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ D,
-                                                                  float* __restrict__ C, int k, float alpha, float beta, float gamma, uint64_t dfields,
+__global__ void __launch_bounds__(THREADS, 1) symm_gemm_tc_kernel(const TcOperands ops, int k, float alpha, float beta, float gamma, uint64_t dfields,
                                                                   unsigned long long* __restrict__ trace) {
+    const float* __restrict__ A = ops.A[blockIdx.y];
+    const float* __restrict__ B = ops.B[blockIdx.y];
+    const float* __restrict__ D = ops.D[blockIdx.y];
+    float* __restrict__ C = ops.C[blockIdx.y];
     using G = Cfg<SPLITK>;
     constexpr int STAGES = G::STAGES, ROWS = G::ROWS;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -356,8 +368,7 @@ static bool env_flag(const char* name, bool dflt) {
     return e ? e[0] != '0' : dflt;
 }
 
-template <int SPLITK> static void launch(const float* A, const float* B, const float* D, float* C, int k, float alpha, float beta, float gamma,
-                                          unsigned long long* trace) {
+template <int SPLITK> static void launch(const TcOperands& ops, int batch, int k, float alpha, float beta, float gamma, unsigned long long* trace) {
     static bool configured = false;
     auto kern = symm_gemm_tc_kernel<SPLITK>;
     if (!configured) {
@@ -366,7 +377,7 @@ template <int SPLITK> static void launch(const float* A, const float* B, const f
     }
     const int nt = (k + TM - 1) / TM;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(nt * (nt + 1) / 2), 1, SPLITK);
+    cfg.gridDim = dim3((unsigned)(nt * (nt + 1) / 2), (unsigned)batch, SPLITK);
     cfg.blockDim = dim3(THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg<SPLITK>::SMEM;
     cfg.stream = ctx().stream;
@@ -391,7 +402,7 @@ template <int SPLITK> static void launch(const float* A, const float* B, const f
     // TB_TC_DESC_SWAP=1 (debug) exchanges the leading/stride byte offsets of the operand descriptors
     static const bool swap = env_flag("TB_TC_DESC_SWAP", false);
     const uint64_t dfields = swap ? smem_desc_fields(SBO, LBO) : smem_desc_fields(LBO, SBO);
-    TB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, B, D, C, k, alpha, beta, gamma, dfields, trace));
+    TB_CUDA(cudaLaunchKernelEx(&cfg, kern, ops, k, alpha, beta, gamma, dfields, trace));
     count_launch();
 }
 
@@ -402,25 +413,46 @@ bool symm_gemm_tc_usable(const float* A, const float* B, const float* D, const f
     return k >= 4 && k % 4 == 0 && k <= 32768 && al(A) && al(B) && al(C) && (D == nullptr || al(D));
 }
 
-// splitk: 0 = choose, else 1 / 2 / 4
+static int choose_splitk(size_t k, int batch) {
+    // enough CTAs to occupy the machine (one CTA per SM: never more CTAs than SMs), at least two K chunks per CTA
+    const size_t nt = (k + tc::TM - 1) / tc::TM, pairs = nt * (nt + 1) / 2 * (size_t)batch, nk = (k + tc::KC - 1) / tc::KC;
+    static const int cap = [] { const char* e = getenv("TB_TC_MAX_SPLITK"); return e ? atoi(e) : 8; }();
+    int splitk = 1;
+    while (splitk < cap && pairs * (size_t)splitk * 2 <= (size_t)ctx().sm_count && nk / (size_t)(splitk * 2) >= 2) splitk *= 2;
+    return splitk;
+}
+
+static void dispatch(const tc::TcOperands& ops, int batch, size_t k, float alpha, float beta, float gamma, int splitk, unsigned long long* trace) {
+    if (splitk == 0) splitk = choose_splitk(k, batch);
+    switch (splitk) {
+        case 1: tc::launch<1>(ops, batch, (int)k, alpha, beta, gamma, trace); break;
+        case 2: tc::launch<2>(ops, batch, (int)k, alpha, beta, gamma, trace); break;
+        case 4: tc::launch<4>(ops, batch, (int)k, alpha, beta, gamma, trace); break;
+        case 8: tc::launch<8>(ops, batch, (int)k, alpha, beta, gamma, trace); break;
+        default: fail(TB_ERR_ARG, "symm_gemm_tc: splitk must be 0, 1, 2, 4 or 8");
+    }
+}
+
+// splitk: 0 = choose, else 1 / 2 / 4 / 8
 void symm_gemm_tc(const float* A, const float* B, const float* D, float* C, size_t k, float alpha, float beta, float gamma, int splitk,
                   unsigned long long* trace) {
     TB_REQUIRE(symm_gemm_tc_usable(A, B, D, C, k), "tensor-core symmetric GEMM needs k % 4 == 0 and 16-byte aligned matrices");
     TB_REQUIRE(C != A && C != B && C != D, "symm_gemm: the output must not alias an input");
-    if (splitk == 0) {
-        // enough CTAs to occupy the machine, at least two K chunks per CTA
-        const size_t nt = (k + tc::TM - 1) / tc::TM, pairs = nt * (nt + 1) / 2, nk = (k + tc::KC - 1) / tc::KC;
-        static const int cap = [] { const char* e = getenv("TB_TC_MAX_SPLITK"); return e ? atoi(e) : 8; }();
-        splitk = 1;
-        while (splitk < cap && pairs * (size_t)splitk * 2 <= (size_t)ctx().sm_count && nk / (size_t)(splitk * 2) >= 2) splitk *= 2;
+    tc::TcOperands ops{};
+    ops.A[0] = A; ops.B[0] = B; ops.D[0] = D; ops.C[0] = C;
+    dispatch(ops, 1, k, alpha, beta, gamma, splitk, trace);
+}
+
+// two independent products with the same scalars in one launch
+void symm_gemm_tc_pair(const float* const A[2], const float* const B[2], const float* const D[2], float* const C[2], size_t k,
+                       float alpha, float beta, float gamma, int splitk) {
+    tc::TcOperands ops{};
+    for (int i = 0; i < 2; ++i) {
+        TB_REQUIRE(symm_gemm_tc_usable(A[i], B[i], D[i], C[i], k), "tensor-core symmetric GEMM needs k % 4 == 0 and 16-byte aligned matrices");
+        TB_REQUIRE(C[i] != A[i] && C[i] != B[i] && C[i] != D[i], "symm_gemm: the output must not alias an input");
+        ops.A[i] = A[i]; ops.B[i] = B[i]; ops.D[i] = D[i]; ops.C[i] = C[i];
     }
-    switch (splitk) {
-        case 1: tc::launch<1>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
-        case 2: tc::launch<2>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
-        case 4: tc::launch<4>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
-        case 8: tc::launch<8>(A, B, D, C, (int)k, alpha, beta, gamma, trace); break;
-        default: fail(TB_ERR_ARG, "symm_gemm_tc: splitk must be 0, 1, 2, 4 or 8");
-    }
+    dispatch(ops, 2, k, alpha, beta, gamma, splitk, nullptr);
 }
 
 }  // namespace tb
