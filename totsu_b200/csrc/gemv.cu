@@ -437,17 +437,33 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
                         T sum0[NTX], sum1[NTX];
 #pragma unroll
                         for (int q = 0; q < NTX; ++q) { sum0[q] = T(0); sum1[q] = T(0); }
+                        if (rows == TR) {
+                            // full chunk (all but the last row chunk): no per-row predicates, all loads issued up front
+                            Vec16<T> v[KROW];
 #pragma unroll
-                        for (int k = 0; k < KROW; ++k) {
-                            if ((lane + 32 * k) * VEC < rows) {
-                                Vec16<T> v = *reinterpret_cast<const Vec16<T>*>(col + (size_t)(lane + 32 * k) * VEC);
+                            for (int k = 0; k < KROW; ++k) v[k] = *reinterpret_cast<const Vec16<T>*>(col + (size_t)(lane + 32 * k) * VEC);
+#pragma unroll
+                            for (int k = 0; k < KROW; ++k)
 #pragma unroll
                                 for (int q = 0; q < NTX; ++q)
 #pragma unroll
                                     for (int i = 0; i < VEC; ++i) {
-                                        if ((k & 1) == 0) sum0[q] += v.v[i] * xr[q][k * VEC + i];
-                                        else sum1[q] += v.v[i] * xr[q][k * VEC + i];
+                                        if ((k & 1) == 0) sum0[q] += v[k].v[i] * xr[q][k * VEC + i];
+                                        else sum1[q] += v[k].v[i] * xr[q][k * VEC + i];
                                     }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < KROW; ++k) {
+                                if ((lane + 32 * k) * VEC < rows) {
+                                    Vec16<T> v = *reinterpret_cast<const Vec16<T>*>(col + (size_t)(lane + 32 * k) * VEC);
+#pragma unroll
+                                    for (int q = 0; q < NTX; ++q)
+#pragma unroll
+                                        for (int i = 0; i < VEC; ++i) {
+                                            if ((k & 1) == 0) sum0[q] += v.v[i] * xr[q][k * VEC + i];
+                                            else sum1[q] += v.v[i] * xr[q][k * VEC + i];
+                                        }
+                                }
                             }
                         }
 #pragma unroll
