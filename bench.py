@@ -185,6 +185,17 @@ def cpu_reference_leg(spec, steps, warmup, sample_blocks=None, threads=None):
     import totsu_oracle as O
     from totsu_b200 import synth
     cores = threads or os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: give the BLAS pool all host cores back and report what it really uses
+    try:
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=cores)
+        blas = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if blas:
+            cores = max(blas)
+    except Exception:
+        env = os.environ.get("OMP_NUM_THREADS")
+        if env and env.isdigit():
+            cores = min(cores, int(env))
     if spec["kind"] == "qp":
         n, m, p = spec["n"], spec["m"], spec["p"]
         psqrt, q, g, h, a, b = qp_instance(n, m, p, np.float32)
