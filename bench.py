@@ -478,6 +478,7 @@ def main():
     # front-end the matrices - in host memory; scalars cross the boundary every iteration; the solution is read back)
     barrier()
     s = new_session()
+    barrier()                            # session construction differs per rank: start the end-to-end clock together
     t0 = time.perf_counter()
     st = s.begin(max_iter=steps, eps_acc=0.0, eps_inf=0.0, device_precond=not qp_stock)
     assert st == "None"
