@@ -57,3 +57,18 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "iterations/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("socp_small")
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches `bench.py --impl reference` like the GPU arm (torchrun for N > 1): rank 0 alone times the CPU
+    path (with the BLAS pool restored: torchrun exports OMP_NUM_THREADS=1) and prints the line, the other ranks exit 0."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29431",
+           os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "socp_small_128x64_A8192x4096",
+           "--steps", "3", "--warmup", "3", "--cpu-sample-blocks", "4"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0
+    assert d["cpu_baseline"]["cores"] >= 1 and (os.cpu_count() == 1 or d["cpu_baseline"]["cores"] > 1)
