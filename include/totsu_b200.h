@@ -56,6 +56,9 @@ int         tb_launch_count(uint64_t* out);
  * roofline: enable, run, then read (launch count, summed kernel milliseconds, summed algorithmic bytes). */
 int         tb_prof_enable(int on);
 int         tb_prof_read(uint64_t* launches, double* total_ms, double* total_bytes);
+/* the same records split by kernel variant: index NN * 3 + NT of stream_kernel<T, NN, NT> (NN / NT = number of A*x / A^T*x
+ * products served by the one read of A: 3 = <1,0>, 1 = <0,1>, 4 = <1,1> pair, 8 = <2,2> pair + speculated pair); arrays of 9 */
+int         tb_prof_read_variants(uint64_t* launches9, double* ms9, double* bytes9);
 /* tuning knob for tests: 0 = auto, 1 = force the generic (LDG) matvec, 2 = force the TMA matvec where legal */
 int         tb_set_gemv_path(int mode);
 /* Lazy op/trans_op pairing (default on): tb_denseop_apply parks the call until the opposite-direction apply on the

@@ -59,6 +59,7 @@ def _signatures():
         "tb_set_speculation": (i, [i]), "tb_spec_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "tb_set_vprog": (i, [i]), "tb_vprog_stats": (i, [C.POINTER(u64), C.POINTER(u64)]), "tb_flush": (i, []),
         "tb_prof_enable": (i, [i]), "tb_prof_read": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "tb_prof_read_variants": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "tb_buf_wrap": (i, [i, vp, sz, i, C.POINTER(H)]), "tb_buf_alloc": (i, [i, sz, C.POINTER(H)]),
         "tb_buf_release": (i, [H]), "tb_buf_retain": (i, [H, i]), "tb_view_of_host": (i, [i, vp, sz, C.POINTER(View)]), "tb_buf_len": (i, [H, C.POINTER(sz)]),
         "tb_host_ref": (i, [View]), "tb_host_mut": (i, [View]),

@@ -11,6 +11,8 @@
 #include <initializer_list>
 #include <stdexcept>
 #include <algorithm>
+#include <mutex>
+#include <map>
 #include "../../include/totsu_b200.h"
 
 namespace tb {
@@ -161,7 +163,10 @@ struct Context {
     static constexpr int kSmallSlots = 1024;
     uint64_t launches = 0;
     uint64_t buf_gen = 0;
-    tb_handle last_lookup = 0;
+    // wrapped host ranges by start address (tb_view_of_host): O(log #buffers) per operand instead of a scan of the table,
+    // which matters on the stock front-end routes (ProbSOCP wraps one MatOp array per cone block)
+    std::multimap<const char*, tb_handle> host_index;
+    size_t host_max_bytes = 0;           // longest wrapped range so far: bounds the backward walk of a lookup
     int gemv_mode = 0;
     bool psd_pairing = true;             // park the first ConePSD projection of an iteration and batch it with the second (cone.cu)
     uint64_t psd_pairs = 0;
@@ -170,10 +175,9 @@ struct Context {
     size_t eig_scratch_bytes = 0;
     // event-pair profiling of the streaming matvec
     bool prof_on = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pairs;   // recorded, not yet read
+    struct ProfRec { cudaEvent_t e0, e1; int variant; double bytes; };   // variant = NN * 3 + NT of stream_kernel<T, NN, NT>
+    std::vector<ProfRec> prof_recs;      // recorded, not yet read
     std::vector<cudaEvent_t> prof_pool;
-    uint64_t prof_launches = 0;
-    double prof_ms = 0.0, prof_bytes = 0.0;
     std::vector<DenseOp*> denseops;
     std::vector<ConeSet*> cones;
     // deferred commands (see "lazy op/trans_op pairing" below); non-empty only while queue[0] is a dense apply
@@ -187,10 +191,16 @@ struct Context {
     // distributed
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
-    std::string last_error;
 };
 
 Context& ctx();
+// One lock around every C-ABI entry point.  The reference keeps its managers in thread_local! (cuda_mgr.rs:113,
+// f32cuda_slice.rs:89) because LinAlg has no `self`; here the context is process-global (one process drives one GPU), so
+// calls from several host threads - e.g. cargo's parallel #[test]s - are serialised instead of racing on the buffer
+// table, the deferred-command queue and the host box.  Recursive: an entry point may run deferred commands that re-enter.
+std::recursive_mutex& api_mutex();
+void set_last_error(const std::string& m);      // per host thread
+void bind_thread();                             // the CUDA current device is per host thread: make this thread use the context's
 void require_init();
 
 Buffer& get_buf(tb_handle h);
@@ -224,29 +234,24 @@ void cone_flush_pending();
 
 // API wrapper: translate internal exceptions to status codes.
 template <typename F> inline int api_keep_pending(F f) {
+    std::lock_guard<std::recursive_mutex> lock(api_mutex());
     try {
+        bind_thread();
         f();
         return TB_OK;
     } catch (const Error& e) {
-        ctx().last_error = e.msg;
+        set_last_error(e.msg);
         return e.code;
     } catch (const std::exception& e) {
-        ctx().last_error = e.what();
+        set_last_error(e.what());
         return TB_ERR_STATE;
     }
 }
 template <typename F> inline int api_raw(F f) {
-    try {
+    return api_keep_pending([&] {
         if (g_cone_pending) cone_flush_pending();
         f();
-        return TB_OK;
-    } catch (const Error& e) {
-        ctx().last_error = e.msg;
-        return e.code;
-    } catch (const std::exception& e) {
-        ctx().last_error = e.what();
-        return TB_ERR_STATE;
-    }
+    });
 }
 void queue_drain();     // run every deferred command in program order (context.cu)
 // Default entry-point wrapper: anything deferred runs first, then the call itself - used by every function that

@@ -179,10 +179,36 @@ static void build_items(ConeSet& cs) {
     }
 }
 
+// Everything Cone::proj can reject is rejected HERE, at the call that the binding maps to Err(()) -> ConeFailure
+// (solver.rs:548-549) - before a projection is parked, so that the error cannot surface on a later, unrelated call.
+template <typename T> static void cone_validate(const ConeSet& cs, const tb_view& x, const tb_view& psd_work) {
+    TB_REQUIRE(x.len == cs.total_len, "cone proj: vector length != sum of block lengths");
+    if (x.len > 0) {
+        const Buffer& bx = get_buf(x.buf);
+        TB_REQUIRE(bx.dtype == DT<T>::id, "cone proj: view element type does not match the function suffix");
+        TB_REQUIRE(x.off <= bx.len && x.len <= bx.len - x.off, "cone proj: view out of range");
+    }
+    if (!cs.has_psd) return;
+    size_t need = 0;
+    for (const tb_cone_block& b : cs.blocks) {
+        if (b.type != TB_CONE_PSD || b.len == 0) continue;
+        size_t k = 0;
+        while ((k + 1) * (k + 2) / 2 <= (size_t)b.len) ++k;
+        TB_REQUIRE(k * (k + 1) / 2 == (size_t)b.len, "cone proj: PSD block length is not a triangular number");     // cone_psd.rs:32-38
+        need = std::max(need, (size_t)tb_map_eig_worklen(k));
+    }
+    TB_REQUIRE(psd_work.len >= need, "cone proj: PSD work slice too short (cone_psd.rs:60-63)");
+    if (need > 0) {
+        const Buffer& bw = get_buf(psd_work.buf);
+        TB_REQUIRE(bw.dtype == DT<T>::id, "cone proj: work element type does not match the function suffix");
+        TB_REQUIRE(psd_work.off <= bw.len && psd_work.len <= bw.len - psd_work.off, "cone proj: work view out of range");
+    }
+}
+
 template <typename T> static void cone_proj(tb_handle h, int dual_cone, tb_view x, T eps_zero, tb_view psd_work) {
     require_init();
     ConeSet& cs = get_cone(h);
-    TB_REQUIRE(x.len == cs.total_len, "cone proj: vector length != sum of block lengths");
+    cone_validate<T>(cs, x, psd_work);
     T* px = wptr<T>(x);
     Context& c = ctx();
     if (cs.has_work) {
@@ -258,7 +284,7 @@ static void cone_proj_submit_f32(tb_handle h, int dual, tb_view x, float eps, tb
     require_init();
     if (!ctx().queue.empty()) queue_drain();
     ConeSet& cs = get_cone(h);
-    TB_REQUIRE(x.len == cs.total_len, "cone proj: vector length != sum of block lengths");
+    cone_validate<float>(cs, x, w);
     if (g_cone_pending) {
         const PendingProj p0 = g_pending;
         const bool pairable = p0.h == h && views_disjoint(p0.x, x) && p0.w.buf == w.buf && p0.w.off == w.off && p0.w.len == w.len &&

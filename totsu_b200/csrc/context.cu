@@ -13,6 +13,20 @@ namespace tb {
 static Context g_ctx;
 Context& ctx() { return g_ctx; }
 
+std::recursive_mutex& api_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+static thread_local std::string t_last_error;
+void set_last_error(const std::string& m) { t_last_error = m; }
+static thread_local int t_bound_device = -1;
+void bind_thread() {
+    if (g_ctx.inited && t_bound_device != g_ctx.device) {
+        TB_CUDA(cudaSetDevice(g_ctx.device));
+        t_bound_device = g_ctx.device;
+    }
+}
+
 void require_init() {
     if (!g_ctx.inited) fail(TB_ERR_STATE, "tb_init has not been called");
 }
@@ -223,6 +237,7 @@ int tb_init(int device) {
         TB_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) fail(TB_ERR_UNSUPPORTED, std::string("totsu_b200 is built for sm_100a (B200); found ") + prop.name);
         c.device = device;
+        t_bound_device = device;
         c.sm_count = prop.multiProcessorCount;
         TB_CUDA(cudaStreamCreateWithFlags(&c.stream.raw, cudaStreamNonBlocking));
         vp_init();
@@ -262,6 +277,7 @@ int tb_shutdown(void) {
             if (b.alive && b.small_slot < 0 && b.dev) cudaFree(b.dev);
         c.bufs.clear();
         c.free_ids.clear();
+        c.host_index.clear();
         if (c.scratch) cudaFree(c.scratch);
         c.scratch = nullptr;
         c.scratch_bytes = 0;
@@ -278,7 +294,7 @@ int tb_shutdown(void) {
     });
 }
 
-const char* tb_last_error(void) { return ctx().last_error.c_str(); }
+const char* tb_last_error(void) { return t_last_error.c_str(); }
 
 int tb_device_sync(void) {
     return api([&] {
@@ -358,6 +374,35 @@ int tb_buf_wrap(int dtype, void* host, size_t len, int host_is_mut, tb_handle* o
         require_init();
         TB_REQUIRE(dtype == TB_F32 || dtype == TB_F64, "bad dtype");
         TB_REQUIRE(host != nullptr || len == 0, "null host pointer");
+        if (!host_is_mut && len > 0) {
+            // The reference may wrap the same read-only array twice at once (ProbSOCP::problem: mats_g[i].as_op() for op_a and
+            // again for the cone's dimensions, socp.rs:450,463): share one mirror instead of uploading and storing it twice,
+            // so that retain / release of either wrapper land on the same refcount.
+            Context& c = ctx();
+            for (size_t i = 0; i < c.bufs.size(); ++i) {
+                Buffer& o = c.bufs[i];
+                if (o.alive && !o.host_mut && o.host == (char*)host && o.len == len && o.dtype == dtype) {
+                    o.refs += 1;
+                    *out = (tb_handle)(i + 1);
+                    return;
+                }
+            }
+        }
+        if (host_is_mut && len > 0) {
+            // a mutable wrap must not partially overlap another live mirror: two device copies of one host range cannot be
+            // kept coherent (an identical or enclosing range is what nested wrappers produce and resolves to the newest)
+            Context& c = ctx();
+            const char* lo = (const char*)host;
+            const char* hi = lo + len * (dtype == TB_F32 ? 4 : 8);
+            for (const Buffer& o : c.bufs) {
+                if (!o.alive || !o.host || o.len == 0) continue;
+                const char* olo = o.host;
+                const char* ohi = o.host + o.len * o.esize;
+                const bool overlap = lo < ohi && olo < hi;
+                const bool nested = (olo <= lo && hi <= ohi) || (lo <= olo && ohi <= hi);
+                if (overlap && !nested) fail(TB_ERR_ARG, "tb_buf_wrap: mutable host range partially overlaps another wrapped slice");
+            }
+        }
         tb_handle h = new_handle();
         Buffer& b = ctx().bufs[(size_t)h - 1];
         b = Buffer();
@@ -374,6 +419,10 @@ int tb_buf_wrap(int dtype, void* host, size_t len, int host_is_mut, tb_handle* o
         }
         b.alive = true;
         b.gen = ++ctx().buf_gen;
+        if (len > 0) {
+            ctx().host_index.emplace(b.host, h);
+            ctx().host_max_bytes = std::max(ctx().host_max_bytes, len * b.esize);
+        }
         if (len > 0) b.host_newer.add(0, len);   // uploaded on first device use (or right away for big read-only data)
         if (!b.host_mut && len * b.esize >= (size_t(1) << 20)) {
             tb_view v{h, 0, len};
@@ -407,13 +456,23 @@ int tb_buf_alloc(int dtype, size_t len, tb_handle* out) {
 }
 
 int tb_buf_release(tb_handle h) {
-    return api([&] {
+    // dropping one of several live wrappers (a split child of the binding) is pure bookkeeping: it must not run a parked
+    // dense apply or cone projection, or op/trans_op pairing could never fire behind `splitm!` (slicelike.rs:162-201)
+    return api_keep_pending([&] {
         require_init();
+        Buffer& b0 = get_buf(h);
+        if (b0.refs > 1) { b0.refs -= 1; return; }
+        if (g_cone_pending) cone_flush_pending();
+        if (!ctx().queue.empty()) queue_drain();
         Buffer& b = get_buf(h);
         Context& c = ctx();
-        if (--b.refs > 0) return;                 // sub-slice wrappers of the binding are still alive
+        if (--b.refs > 0) return;
         spec_note_release(h);
-        if (c.last_lookup == h) c.last_lookup = 0;
+        if (b.host && b.len > 0) {
+            auto range = c.host_index.equal_range(b.host);
+            for (auto it = range.first; it != range.second; ++it)
+                if (it->second == h) { c.host_index.erase(it); break; }
+        }
         if (b.host && b.host_mut) host_sync_range(b, 0, b.len);
         if (b.small_slot >= 0) {
             // slab slots are recycled without a device sync: every use is stream-ordered
@@ -428,7 +487,7 @@ int tb_buf_release(tb_handle h) {
 }
 
 int tb_buf_retain(tb_handle h, int n) {
-    return api([&] {
+    return api_keep_pending([&] {         // bookkeeping only: nothing deferred has to run first
         require_init();
         TB_REQUIRE(n >= 0, "retain count must be >= 0");
         get_buf(h).refs += n;
@@ -436,7 +495,10 @@ int tb_buf_retain(tb_handle h, int n) {
 }
 
 int tb_view_of_host(int dtype, const void* host, size_t len, tb_view* out) {
-    return api([&] {
+    // A pure table lookup: the binding resolves EVERY operand of EVERY call through it (rust/totsu_b200/src/b200_slice.rs
+    // `view()`), also between the two halves of an op/trans_op pair and between the two cone projections of an iteration,
+    // so it must neither drain the deferred-command queue nor run a parked projection.
+    return api_keep_pending([&] {
         require_init();
         Context& c = ctx();
         if (len == 0) { *out = tb_view{0, 0, 0}; return; }
@@ -446,16 +508,19 @@ int tb_view_of_host(int dtype, const void* host, size_t len, tb_view* out) {
         auto covers = [&](const Buffer& b) {
             return b.alive && b.host && b.dtype == dtype && b.host <= lo && hi <= b.host + b.len * b.esize;
         };
+        // nearest wrapped range starting at or below `lo` that covers [lo, hi); among wrappers of the same start address the
+        // newest wins (a stack slot re-wrapped every iteration, solver.rs:590-591)
         tb_handle best = 0;
-        if (c.last_lookup > 0 && (size_t)c.last_lookup <= c.bufs.size() && covers(c.bufs[(size_t)c.last_lookup - 1])) {
-            best = c.last_lookup;
-        } else {
-            uint64_t best_gen = 0;
-            for (size_t i = 0; i < c.bufs.size(); ++i)
-                if (covers(c.bufs[i]) && c.bufs[i].gen > best_gen) { best = (tb_handle)(i + 1); best_gen = c.bufs[i].gen; }
+        uint64_t best_gen = 0;
+        const char* best_start = nullptr;
+        for (auto it = c.host_index.upper_bound(lo); it != c.host_index.begin();) {
+            --it;
+            if (best != 0 && it->first != best_start) break;
+            if ((size_t)(lo - it->first) > c.host_max_bytes) break;
+            const Buffer& b = c.bufs[(size_t)it->second - 1];
+            if (covers(b) && b.gen > best_gen) { best = it->second; best_gen = b.gen; best_start = it->first; }
         }
         if (best == 0) fail(TB_ERR_ARG, "tb_view_of_host: the host range is not inside any wrapped slice");
-        c.last_lookup = best;
         const Buffer& b = c.bufs[(size_t)best - 1];
         *out = tb_view{best, (size_t)(lo - b.host) / es, len};
     });

@@ -528,8 +528,7 @@ template <typename T, int NN, int NT> static void launch_stream(const StreamPara
     TB_LAUNCH_CHECK();
     if (c.prof_on) {
         TB_CUDA(cudaEventRecord(e1, c.stream));
-        c.prof_pairs.push_back({e0, e1});
-        c.prof_bytes += (double)p.n_row * (double)p.n_col * sizeof(T);     // one read of A
+        c.prof_recs.push_back({e0, e1, NN * 3 + NT, (double)p.n_row * (double)p.n_col * sizeof(T)});     // one read of A
     }
 }
 
@@ -999,23 +998,37 @@ int tb_prof_enable(int on) {
         ctx().prof_on = on != 0;
     });
 }
+// reads and clears the records: per-variant sums into l9 / ms9 / b9 (index NN * 3 + NT), any of which may be null
+static void prof_collect(uint64_t* l9, double* ms9, double* b9) {
+    require_init();
+    Context& c = ctx();
+    TB_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < 9; ++i) {
+        if (l9) l9[i] = 0;
+        if (ms9) ms9[i] = 0.0;
+        if (b9) b9[i] = 0.0;
+    }
+    for (auto& pr : c.prof_recs) {
+        float ms = 0.f;
+        TB_CUDA(cudaEventElapsedTime(&ms, pr.e0, pr.e1));
+        if (l9) l9[pr.variant] += 1;
+        if (ms9) ms9[pr.variant] += ms;
+        if (b9) b9[pr.variant] += pr.bytes;
+        c.prof_pool.push_back(pr.e0);
+        c.prof_pool.push_back(pr.e1);
+    }
+    c.prof_recs.clear();
+}
 int tb_prof_read(uint64_t* launches, double* total_ms, double* total_bytes) {
     return api([&] {
-        require_init();
-        Context& c = ctx();
-        TB_CUDA(cudaStreamSynchronize(c.stream));
-        for (auto& pr : c.prof_pairs) {
-            float ms = 0.f;
-            TB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
-            c.prof_ms += ms;
-            c.prof_launches += 1;
-            c.prof_pool.push_back(pr.first);
-            c.prof_pool.push_back(pr.second);
-        }
-        c.prof_pairs.clear();
-        *launches = c.prof_launches; *total_ms = c.prof_ms; *total_bytes = c.prof_bytes;
-        c.prof_launches = 0; c.prof_ms = 0.0; c.prof_bytes = 0.0;
+        uint64_t l9[9]; double ms9[9], b9[9];
+        prof_collect(l9, ms9, b9);
+        *launches = 0; *total_ms = 0.0; *total_bytes = 0.0;
+        for (int i = 0; i < 9; ++i) { *launches += l9[i]; *total_ms += ms9[i]; *total_bytes += b9[i]; }
     });
+}
+int tb_prof_read_variants(uint64_t* launches9, double* ms9, double* bytes9) {
+    return api([&] { prof_collect(launches9, ms9, bytes9); });
 }
 
 int tb_transform_ge_f32(int tr, size_t nr, size_t nc, float a, tb_view m, tb_view x, float b, tb_view y) {
@@ -1036,6 +1049,8 @@ int tb_denseop_create(int dtype, tb_view mat, size_t n_row, size_t n_col, size_t
         if (c.world > 1 && n_row != n_row_total)
             TB_REQUIRE(n_row * (size_t)c.world == n_row_total && row_offset == n_row * (size_t)c.rank,
                        "denseop: row shards must be equal-sized and rank-ordered");
+        else       // not sharded: the operator IS the whole matrix (a partial one would silently leave rows of y untouched)
+            TB_REQUIRE(n_row == n_row_total && row_offset == 0, "denseop: a row shard needs tb_dist_init with world > 1");
         (void)dev_ptr(mat, dtype, false);
         void* tmp = nullptr;
         if (c.world > 1 && n_row != n_row_total) TB_CUDA(cudaMalloc(&tmp, std::max<size_t>(n_col, 1) * (dtype == TB_F32 ? 4 : 8)));

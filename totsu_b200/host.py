@@ -60,8 +60,16 @@ def hlib():
         L.tbh_session_norms.argtypes = [vp, C.POINTER(d), C.POINTER(d)]
         L.tbh_session_destroy.argtypes = [vp]
         L.tbh_session_destroy.restype = None
+        L.tbh_set_shim_protocol.argtypes = [i]
+        L.tbh_set_shim_protocol.restype = None
+        L.tbh_get_shim_protocol.restype = i
         _hlib = L
     return _hlib
+
+
+def set_shim_protocol(on):
+    """Drive the backend with the Rust binding's call protocol (see totsu_b200/host/linalg.hpp); set before creating sessions."""
+    hlib().tbh_set_shim_protocol(1 if on else 0)
 
 
 def _p(a):

@@ -274,6 +274,11 @@ extern "C" {
 
 const char* tbh_last_error(void) { return g_err.c_str(); }
 
+// 1: issue the Rust binding's call protocol (tb_view_of_host per operand, tb_buf_retain / tb_buf_release per split child;
+// host/linalg.hpp "shim-protocol mode"); 0: carry (handle, offset, length) views.  Set before sessions are created.
+void tbh_set_shim_protocol(int on) { shim_protocol() = on != 0; }
+int tbh_get_shim_protocol(void) { return shim_protocol() ? 1 : 0; }
+
 void* tbh_session_lp(int dtype, size_t n, size_t m, size_t p, const void* c, const void* g, const void* h, const void* a, const void* b) {
     return guarded_new([&] { return (void*)DISPATCH(dtype, make_lp, n, m, p, c, g, h, a, b); });
 }

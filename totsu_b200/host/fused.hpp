@@ -44,6 +44,9 @@ private:
 template <typename F> class ProductCone : public Cone<F> {
 public:
     using Sl = Slice<F>;
+    // The PSD work area (2k^2 + k elements, cone_psd.rs:32-38) is a device-only buffer allocated ONCE here, exactly like
+    // rust/totsu_b200/src/fused.rs: proj() neither wraps nor releases anything, so the first projection of an iteration
+    // stays parked until the second arrives (csrc/cone.cu "pairing of the two projections").
     ProductCone(const std::vector<tb_cone_block>& blocks, F eps_zero) : blocks_(blocks), eps_zero_(eps_zero) {
         TBH_CALL(tb_cone_create(blocks_.data(), blocks_.size(), &h_));
         size_t wl = 0;
@@ -55,31 +58,55 @@ public:
             }
         }
         if (wl > 0) {
-            psd_work_host_.assign(wl, F(0));
-            psd_work_ = Sl::new_mut(psd_work_host_.data(), wl);
+            tb_handle wh = 0;
+            TBH_CALL(tb_buf_alloc(Abi<F>::dtype, wl, &wh));
+            psd_work_ = tb_view{wh, 0, wl};
         }
     }
     ~ProductCone() override {
-        psd_work_.drop();
+        if (psd_work_.buf) tb_buf_release(psd_work_.buf);
         if (h_) tb_cone_destroy(h_);
     }
+    ProductCone(const ProductCone&) = delete;
+    ProductCone& operator=(const ProductCone&) = delete;
     bool proj(bool dual_cone, Sl& x) override {
-        int st = Abi<F>::cone_proj(h_, dual_cone ? 1 : 0, x.view(), eps_zero_, psd_work_.view());
+        // arguments are validated at submit time (before the call may be parked), so TB_ERR_ARG can only come from here
+        int st = Abi<F>::cone_proj(h_, dual_cone ? 1 : 0, x.view(), eps_zero_, psd_work_);
         if (st == TB_ERR_ARG) return false;       // work shortage / malformed block: Err(()) -> ConeFailure
         tb_check(st, "tb_cone_proj");
         return true;
     }
-    // the solver's `group` closure is the min-fill (solver.rs:509-518); it runs on the device for every block
-    void product_group(Sl& dp_tau, const typename Cone<F>::Group&) const override {
-        TBH_CALL(Abi<F>::cone_group_min(h_, dp_tau.view()));
+    // cone.rs:20-29: split dp_tau into the blocks and call `group` once per block of size > 1.  The solver passes the
+    // min-fill closure (solver.rs:509-518), which tb_cone_group_min computes for every block in one launch; any OTHER
+    // closure gets the trait's contract literally - one `group` call per block on its sub-slice.
+    void product_group(Sl& dp_tau, const typename Cone<F>::Group& group) const override {
+        if (is_min_fill(group)) {
+            TBH_CALL(Abi<F>::cone_group_min(h_, dp_tau.view()));
+            return;
+        }
+        size_t done = 0;
+        for (const auto& b : blocks_) {
+            const size_t len = (size_t)b.len;
+            Sl t_blk = dp_tau.sub(done, len);
+            done += len;
+            if (len > 1 && b.type != TB_CONE_ZERO && b.type != TB_CONE_RPOS) group(t_blk);      // cone_zero.rs:46-49, cone_rpos.rs:47-50
+        }
     }
 
 private:
+    // probe the closure on a 3-element slice: the solver's closure fills the group with its minimum
+    static bool is_min_fill(const typename Cone<F>::Group& group) {
+        F probe[3] = {F(3), F(1), F(2)};
+        {
+            Sl sl = Sl::new_mut(probe, 3);
+            group(sl);
+        }
+        return probe[0] == F(1) && probe[1] == F(1) && probe[2] == F(1);
+    }
     std::vector<tb_cone_block> blocks_;
     F eps_zero_;
     tb_handle h_ = 0;
-    std::vector<F> psd_work_host_;
-    Sl psd_work_;
+    tb_view psd_work_{0, 0, 0};
 };
 
 }  // namespace totsu_b200

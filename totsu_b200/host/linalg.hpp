@@ -66,6 +66,19 @@ TBH_ABI(double, f64)
 #undef TBH_ABI
 
 // ---------------------------------------------------------------------------------------------------------
+// "Shim-protocol" mode.  The Rust binding's slice type IS the host sub-slice (rust/totsu_b200/src/b200_slice.rs: a
+// transparent wrapper of `[F]`), so it carries no handle: every operand of every call is resolved with
+// tb_view_of_host, every split child takes a reference on its root (tb_buf_retain) and gives it back when it drops
+// (tb_view_of_host + tb_buf_release).  This mirror normally carries (handle, offset, length) views instead, which skips
+// those calls.  With shim_protocol() on it issues exactly the binding's call sequence - and checks that each lookup
+// resolves to the view it carries - so that what is tested and measured here transfers to `Solver<B200>`.
+// ---------------------------------------------------------------------------------------------------------
+inline bool& shim_protocol() {
+    static bool on = false;
+    return on;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Slice<F>: SliceLike.  A root slice (new_ref / new_mut) owns a device mirror of caller memory and restores
 // host coherence when dropped (slicelike.rs:18-19); split slices are plain (handle, offset, length) views.
 // ---------------------------------------------------------------------------------------------------------
@@ -79,7 +92,8 @@ public:
         if (this != &o) {
             drop();
             v_ = o.v_; root_ = o.root_; host_ = o.host_; mut_ = o.mut_;
-            o.root_ = false; o.v_ = tb_view{0, 0, 0};
+            child_ = o.child_; rest_host_ = o.rest_host_; rest_len_ = o.rest_len_;
+            o.root_ = false; o.v_ = tb_view{0, 0, 0}; o.child_ = false; o.rest_len_ = 0;
         }
         return *this;
     }
@@ -109,10 +123,80 @@ public:
     // split_ref / split_mut (slicelike.rs:31-37)
     std::pair<Slice, Slice> split(size_t mid) const {
         if (mid > v_.len) throw BackendError("split: mid > len");
-        return {sub(0, mid), sub(mid, v_.len - mid)};
+        Slice a = raw_sub(0, mid), b = raw_sub(mid, v_.len - mid);
+        if (shim_protocol() && host_) {                          // b200_slice.rs split_ref / split_mut
+            const int n = (mid > 0) + (v_.len - mid > 0);
+            if (n > 0) TBH_CALL(tb_buf_retain(view().buf, n));
+            a.child_ = mid > 0;
+            b.child_ = v_.len - mid > 0;
+        }
+        return {std::move(a), std::move(b)};
     }
-    // the splitm! / splitm_mut! macros (slicelike.rs:162-201) reduce to taking sub-ranges
+    // One step of the splitm! / splitm_mut! macros (slicelike.rs:162-201): `(part; len)` at the front of what is left of
+    // the parent.  In shim-protocol mode this is ONE split of the binding: its two children are `part` and the remainder,
+    // both released when `part` goes out of scope (the macro keeps the remainder alive exactly as long).
     Slice sub(size_t off, size_t len) const {
+        Slice r = raw_sub(off, len);
+        if (shim_protocol() && host_) {
+            const size_t rest = v_.len - (off + len);
+            const int n = (len > 0) + (rest > 0);
+            if (n > 0) TBH_CALL(tb_buf_retain(view().buf, n));
+            r.child_ = len > 0;
+            r.rest_host_ = host_ + off + len;
+            r.rest_len_ = rest;
+        }
+        return r;
+    }
+    // SliceLike::drop (slicelike.rs:41): only the root has anything to reconcile
+    void drop() {
+        if (root_ && v_.buf > 0) {
+            tb_buf_release(shim_protocol() && host_ && v_.len > 0 ? view().buf : v_.buf);
+            root_ = false;
+            v_ = tb_view{0, 0, 0};
+        }
+        if (child_) {                                            // b200_slice.rs drop(): resolve, then release
+            child_ = false;
+            tb_view cv{0, 0, 0};
+            if (tb_view_of_host(Abi<F>::dtype, host_, v_.len, &cv) == TB_OK) tb_buf_release(cv.buf);
+        }
+        if (rest_len_ > 0) {
+            tb_view rv{0, 0, 0};
+            if (tb_view_of_host(Abi<F>::dtype, rest_host_, rest_len_, &rv) == TB_OK) tb_buf_release(rv.buf);
+            rest_len_ = 0;
+        }
+    }
+    size_t len() const { return v_.len; }                        // slicelike.rs:44
+    const F* get_ref() const {                                   // slicelike.rs:47
+        if (!host_) throw BackendError("get_ref on a device-only slice");
+        TBH_CALL(tb_host_ref(view()));
+        return host_;
+    }
+    F* get_mut() {                                               // slicelike.rs:50
+        if (!host_ || !mut_) throw BackendError("get_mut on a read-only slice");
+        TBH_CALL(tb_host_mut(view()));
+        return host_;
+    }
+    F get(size_t idx) const {                                    // slicelike.rs:54-59
+        F out;
+        TBH_CALL(Abi<F>::get1(view(), idx, &out));
+        return out;
+    }
+    void set(size_t idx, F val) {                                // slicelike.rs:63-68
+        TBH_CALL(Abi<F>::set1(view(), idx, val));
+    }
+    // the device view of this slice; in shim-protocol mode resolved from the host address like B200Slice::view()
+    tb_view view() const {
+        if (shim_protocol() && host_ && v_.len > 0) {
+            tb_view v{0, 0, 0};
+            TBH_CALL(tb_view_of_host(Abi<F>::dtype, host_, v_.len, &v));
+            if (v.buf != v_.buf || v.off != v_.off || v.len != v_.len) throw BackendError("shim protocol: tb_view_of_host resolved to a different view");
+            return v;
+        }
+        return v_;
+    }
+
+private:
+    Slice raw_sub(size_t off, size_t len) const {
         if (off > v_.len || len > v_.len - off) throw BackendError("sub-slice out of range");
         Slice r;
         r.v_ = tb_view{v_.buf, v_.off + off, len};
@@ -121,40 +205,15 @@ public:
         r.mut_ = mut_;
         return r;
     }
-    // SliceLike::drop (slicelike.rs:41): only the root has anything to reconcile
-    void drop() {
-        if (root_ && v_.buf > 0) {
-            tb_buf_release(v_.buf);
-            root_ = false;
-            v_ = tb_view{0, 0, 0};
-        }
-    }
-    size_t len() const { return v_.len; }                        // slicelike.rs:44
-    const F* get_ref() const {                                   // slicelike.rs:47
-        if (!host_) throw BackendError("get_ref on a device-only slice");
-        TBH_CALL(tb_host_ref(v_));
-        return host_;
-    }
-    F* get_mut() {                                               // slicelike.rs:50
-        if (!host_ || !mut_) throw BackendError("get_mut on a read-only slice");
-        TBH_CALL(tb_host_mut(v_));
-        return host_;
-    }
-    F get(size_t idx) const {                                    // slicelike.rs:54-59
-        F out;
-        TBH_CALL(Abi<F>::get1(v_, idx, &out));
-        return out;
-    }
-    void set(size_t idx, F val) {                                // slicelike.rs:63-68
-        TBH_CALL(Abi<F>::set1(v_, idx, val));
-    }
-    tb_view view() const { return v_; }
-
-private:
     tb_view v_{0, 0, 0};
     bool root_ = false;
     F* host_ = nullptr;
     bool mut_ = false;
+    // shim-protocol bookkeeping: this wrapper holds one reference on its root (child_), and one more for the remainder
+    // sibling of the split that produced it (rest_host_, rest_len_)
+    bool child_ = false;
+    F* rest_host_ = nullptr;
+    size_t rest_len_ = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------
