@@ -183,6 +183,51 @@ def test_denseop_apply_pair_absadd(dt, shape):
     abuf.release()
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(2048, 640), (5000, 333), (1028, 2050)])
+@pytest.mark.parametrize("rows_first", [False, True])
+def test_one_pass_absadd_and_invalidation(dt, shape, rows_first):
+    """absadd_cols + absadd_rows of a streaming-size operator come from ONE read of A (stream_kernel<T,1,1,ABS>): whichever
+    is asked for first computes both sums of |A|, the other is served from the kept sums (matop.rs:98-138 semantics:
+    tau[c] += sum_r |A[r,c]|, sigma[r] += sum_c |A[r,c]|); a write into the matrix drops the kept sums."""
+    m, n = shape
+    L = capi.lib()
+    rng = np.random.default_rng(m + n)
+    a = np.asfortranarray(rng.standard_normal((m, n)).astype(dt))
+    abuf, av = device_matrix(a)
+    h = C.c_int64()
+    capi.check(L.tb_denseop_create(capi.dtype_id(dt), av, m, n, 0, 0, C.byref(h)))
+    capi.check(L.tb_set_gemv_path(2))
+    tol = 3e-5 if dt == np.float32 else 1e-12
+
+    def both(mat):
+        tau, sig = rng.standard_normal(n).astype(dt), rng.standard_normal(m).astype(dt)
+        t0, s0 = tau.astype(np.float64), sig.astype(np.float64)
+        bt_, bs_ = capi.Buf(tau), capi.Buf(sig)
+        l0 = capi.launch_count()
+        calls = [("tb_denseop_absadd_rows", bs_), ("tb_denseop_absadd_cols", bt_)] if rows_first else [("tb_denseop_absadd_cols", bt_), ("tb_denseop_absadd_rows", bs_)]
+        for name, bf in calls:
+            capi.check(capi.fn(name, dt)(h.value, bf.view()))
+        capi.check(L.tb_flush())
+        launches = capi.launch_count() - l0
+        bt_.release(); bs_.release()
+        a64 = mat.astype(np.float64)
+        assert rel_linf(tau, t0 + np.abs(a64).sum(0)) <= tol
+        assert rel_linf(sig, s0 + np.abs(a64).sum(1)) <= tol
+        return launches
+    try:
+        first = both(a)
+        again = both(a)                       # served from the kept sums: no pass over A at all
+        assert again < first
+        a2 = np.asfortranarray(rng.standard_normal((m, n)).astype(dt))
+        abuf.upload(a2.reshape(-1, order="F"))   # the matrix changes: the kept sums must not be reused
+        both(a2)
+    finally:
+        capi.check(L.tb_set_gemv_path(0))
+        capi.check(L.tb_denseop_destroy(h.value))
+        abuf.release()
+
+
 def test_full_size_properties_c3():
     """BASELINE config C3 (A 65536 x 16384, f32, generated in HBM): properties that need no CPU copy of A -
     adjoint identity <A x, y> = <x, A^T y>, linearity in x, fused pair == separate calls, run-to-run bit

@@ -300,7 +300,9 @@ struct StreamParams {
 
 // NN / NT: how many N passes (y = A x) and T passes (y = A^T x) are served by this one read of A (0..2 each).  <1,1> is
 // an op/trans_op pair; <2,2> adds the speculated products of the NEXT pair (see "speculative pairing" below).
-template <typename T, int NN, int NT>
+// ABS: the products are taken with |A| and x == 1 (no x is read): one pass yields the row sums AND the column sums of |A|,
+// i.e. Operator::absadd_rows and absadd_cols (matop.rs:98-138) from a single read of A.
+template <typename T, int NN, int NT, bool ABS = false>
 __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamParams p) {
     using Cfg = StreamCfg<T>;
     constexpr int VEC = Cfg::VEC;
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
             const size_t c1 = c1e < p.n_col ? c1e : p.n_col;
             const int ucols = (int)(c1 - c0);
 
-            if (NN > 0) {
+            if (NN > 0 && !ABS) {
                 // stage this unit's slice of x (previous unit's readers are done: barrier first)
                 ptx::named_bar_sync(1, kConsumers);
 #pragma unroll
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
             }
             // pass T: x chunk for the rows this lane strides over, rows beyond the matrix read as 0
             T xr[NTX][KROW * VEC];
-            if (NT > 0) {
+            if (NT > 0 && !ABS) {
 #pragma unroll
                 for (int q = 0; q < NTX; ++q) {
                     const T* __restrict__ x_t = reinterpret_cast<const T*>(p.x_t[q]);
@@ -415,18 +417,23 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
                         for (int q = 0; q < NNX; ++q)
 #pragma unroll
                             for (int j = 0; j < kTC; ++j) {
-                                T xv = xs[q * kMaxUnitCols + cl + j];
+                                if (ABS) {
 #pragma unroll
-                                for (int i = 0; i < VEC; ++i) acc[q][i] += v[j].v[i] * xv;
+                                    for (int i = 0; i < VEC; ++i) acc[q][i] += fabs(v[j].v[i]);
+                                } else {
+                                    T xv = xs[q * kMaxUnitCols + cl + j];
+#pragma unroll
+                                    for (int i = 0; i < VEC; ++i) acc[q][i] += v[j].v[i] * xv;
+                                }
                             }
                     } else {
                         for (int j = 0; j < ncols; ++j) {
                             Vec16<T> v = *reinterpret_cast<const Vec16<T>*>(tile + (size_t)j * TR + tid * VEC);
 #pragma unroll
                             for (int q = 0; q < NNX; ++q) {
-                                T xv = xs[q * kMaxUnitCols + cl + j];
+                                T xv = ABS ? T(1) : xs[q * kMaxUnitCols + cl + j];
 #pragma unroll
-                                for (int i = 0; i < VEC; ++i) acc[q][i] += v.v[i] * xv;
+                                for (int i = 0; i < VEC; ++i) acc[q][i] += (ABS ? fabs(v.v[i]) : v.v[i]) * xv;
                             }
                         }
                     }
@@ -448,8 +455,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
                                 for (int q = 0; q < NTX; ++q)
 #pragma unroll
                                     for (int i = 0; i < VEC; ++i) {
-                                        if ((k & 1) == 0) sum0[q] += v[k].v[i] * xr[q][k * VEC + i];
-                                        else sum1[q] += v[k].v[i] * xr[q][k * VEC + i];
+                                        const T t = ABS ? fabs(v[k].v[i]) : v[k].v[i] * xr[q][k * VEC + i];
+                                        if ((k & 1) == 0) sum0[q] += t;
+                                        else sum1[q] += t;
                                     }
                         } else {
 #pragma unroll
@@ -460,8 +468,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
                                     for (int q = 0; q < NTX; ++q)
 #pragma unroll
                                         for (int i = 0; i < VEC; ++i) {
-                                            if ((k & 1) == 0) sum0[q] += v.v[i] * xr[q][k * VEC + i];
-                                            else sum1[q] += v.v[i] * xr[q][k * VEC + i];
+                                            const T t = ABS ? fabs(v.v[i]) : v.v[i] * xr[q][k * VEC + i];
+                                            if ((k & 1) == 0) sum0[q] += t;
+                                            else sum1[q] += t;
                                         }
                                 }
                             }
@@ -506,10 +515,10 @@ template <typename T> static bool stream_eligible(const T* A, size_t lda, size_t
     return n_row * n_col >= (size_t(1) << 20);
 }
 
-template <typename T, int NN, int NT> static void launch_stream(const StreamParams& p, int grid, size_t smem) {
+template <typename T, int NN, int NT, bool ABS = false> static void launch_stream(const StreamParams& p, int grid, size_t smem) {
     static bool attr_set = false;     // one flag per kernel instantiation
     if (!attr_set) {
-        TB_CUDA(cudaFuncSetAttribute(stream_kernel<T, NN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TB_CUDA(cudaFuncSetAttribute(stream_kernel<T, NN, NT, ABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     Context& c = ctx();
@@ -524,7 +533,7 @@ template <typename T, int NN, int NT> static void launch_stream(const StreamPara
         e0 = get_ev(); e1 = get_ev();
         TB_CUDA(cudaEventRecord(e0, c.stream));
     }
-    stream_kernel<T, NN, NT><<<grid, kStreamThreads, smem, c.stream>>>(p);
+    stream_kernel<T, NN, NT, ABS><<<grid, kStreamThreads, smem, c.stream>>>(p);
     TB_LAUNCH_CHECK();
     if (c.prof_on) {
         TB_CUDA(cudaEventRecord(e1, c.stream));
@@ -572,7 +581,7 @@ static void stream_finalize_partials(const T* part_n, size_t n_splits, const T* 
 template <typename T>
 static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
                        const T* x_n, T alpha_n, T beta_n, T* y_n,
-                       const T* x_t, T alpha_t, T beta_t, T* y_t, bool sharded = false, SpecJob<T>* spec = nullptr) {
+                       const T* x_t, T alpha_t, T beta_t, T* y_t, bool sharded = false, SpecJob<T>* spec = nullptr, bool abs_ones = false) {
     Context& c = ctx();
     constexpr int VEC = StreamCfg<T>::VEC;
     constexpr size_t TR = (size_t)kConsumers * VEC;
@@ -616,6 +625,9 @@ static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
         p.x_n[1] = spec->x_n; p.x_t[1] = spec->x_t;
         p.part_n[1] = spec->part_n; p.part_t[1] = spec->part_t;
         launch_stream<T, 2, 2>(p, grid, smem);
+    } else if (abs_ones) {
+        TB_REQUIRE(do_n && do_t, "internal: the |A| pass produces both sums");
+        launch_stream<T, 1, 1, true>(p, grid, smem);
     } else if (do_n && do_t) launch_stream<T, 1, 1>(p, grid, smem);
     else if (do_n) launch_stream<T, 1, 0>(p, grid, smem);
     else launch_stream<T, 0, 1>(p, grid, smem);
@@ -678,6 +690,10 @@ struct DenseOp {
     size_t n_row, n_col;        // local shard
     size_t row_offset, n_row_total;
     void* tmp_n;                // n_col elements: local partial of A^T x before the all-reduce (sharded only)
+    // one-pass absadd: row sums and column sums of |A| (this rank's rows) from ONE streaming read, kept until A changes
+    void* abs_rows = nullptr;   // n_row elements
+    void* abs_cols = nullptr;   // n_col elements
+    bool abs_valid = false;
 };
 
 static DenseOp& get_op(tb_handle h) {
@@ -776,6 +792,8 @@ static inline bool view_overlaps(const tb_view& v, tb_handle buf, size_t off, si
 
 // called by dev_ptr for every range about to change on the device
 void spec_note_write(tb_handle buf, size_t off, size_t len) {
+    for (DenseOp* op : ctx().denseops)          // cached |A| sums die with any write into their matrix
+        if (op != nullptr && op->abs_valid && view_overlaps(op->mat, buf, off, len)) op->abs_valid = false;
     SpecState& S = g_spec;
     if (!S.valid) return;
     if (view_overlaps(S.sig.xn, buf, off, len) || view_overlaps(S.sig.xt, buf, off, len)) {
@@ -957,16 +975,49 @@ template <typename T> static void denseop_submit(tb_handle h, int transpose, T a
     c.queue.push_back(std::move(cmd));
 }
 
+// Operator::absadd_cols (tau[c] += sum_r |A[r,c]|) and absadd_rows (sigma[r] += sum_c |A[r,c]|), the two halves of
+// SelfDualEmbed::abssum (solver.rs:159-183; per-column / per-row L::abssum loops in MatOp::absadd_impl, matop.rs:98-138).
+// For a matrix the streaming kernel serves, whichever is asked for first runs stream_kernel<T,1,1,ABS> - ONE read of A that
+// yields both the row sums and the column sums of |A| - and the other is served from the kept sums (C3: 0.66 ms for the
+// pair instead of 2.5 + 0.7 ms through the generic kernels).  Any write into the matrix drops the kept sums.
 template <typename T> static void denseop_absadd(tb_handle h, bool cols, tb_view v) {
     require_init();
     DenseOp& op = get_op(h);
     Context& c = ctx();
     TB_REQUIRE(op.dtype == DT<T>::id, "denseop dtype mismatch");
     const T* A = rptr<T>(op.mat);
+    TB_REQUIRE(v.len == (cols ? op.n_col : op.n_row_total), cols ? "absadd_cols: length mismatch" : "absadd_rows: length mismatch");
     T* pv = wptr<T>(v);
     const bool sharded = c.world > 1 && op.n_row != op.n_row_total;
+    if (stream_eligible<T>(A, op.n_row, op.n_row, op.n_col)) {
+        if (!op.abs_rows) TB_CUDA(cudaMalloc(&op.abs_rows, op.n_row * sizeof(T)));
+        if (!op.abs_cols) TB_CUDA(cudaMalloc(&op.abs_cols, op.n_col * sizeof(T)));
+        T* ar = reinterpret_cast<T*>(op.abs_rows);
+        T* ac = reinterpret_cast<T*>(op.abs_cols);
+        if (!op.abs_valid) {
+            run_stream<T>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(0), ar, nullptr, T(1), T(0), ac, false, nullptr, true);
+            op.abs_valid = true;
+        }
+        if (cols) {
+            if (!sharded) {
+                l1_axpby<T>(T(1), ac, T(1), pv, op.n_col);
+            } else {
+                T* tmp = reinterpret_cast<T*>(op.tmp_n);
+                l1_copy<T>(ac, tmp, op.n_col);
+                dist_allreduce_sum(tmp, op.n_col, DT<T>::id);
+                l1_axpby<T>(T(1), tmp, T(1), pv, op.n_col);
+            }
+        } else {
+            if (!sharded) {
+                l1_axpby<T>(T(1), ar, T(1), pv, op.n_row);
+            } else {
+                l1_axpby<T>(T(1), ar, T(1), pv + op.row_offset, op.n_row);
+                dist_allgather_inplace(pv, op.n_row, DT<T>::id);
+            }
+        }
+        return;
+    }
     if (cols) {
-        TB_REQUIRE(v.len == op.n_col, "absadd_cols: length mismatch");
         if (!sharded) {
             run_generic_t<T, true>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(1), pv);
         } else {
@@ -976,7 +1027,6 @@ template <typename T> static void denseop_absadd(tb_handle h, bool cols, tb_view
             l1_axpby<T>(T(1), tmp, T(1), pv, op.n_col);
         }
     } else {
-        TB_REQUIRE(v.len == op.n_row_total, "absadd_rows: length mismatch");
         if (!sharded) {
             run_generic_n<T, true>(A, op.n_row, op.n_row, op.n_col, nullptr, T(1), T(1), pv);
         } else {
@@ -1054,7 +1104,8 @@ int tb_denseop_create(int dtype, tb_view mat, size_t n_row, size_t n_col, size_t
         (void)dev_ptr(mat, dtype, false);
         void* tmp = nullptr;
         if (c.world > 1 && n_row != n_row_total) TB_CUDA(cudaMalloc(&tmp, std::max<size_t>(n_col, 1) * (dtype == TB_F32 ? 4 : 8)));
-        DenseOp* op = new DenseOp{dtype, mat, n_row, n_col, row_offset, n_row_total, tmp};
+        DenseOp* op = new DenseOp();
+        op->dtype = dtype; op->mat = mat; op->n_row = n_row; op->n_col = n_col; op->row_offset = row_offset; op->n_row_total = n_row_total; op->tmp_n = tmp;
         c.denseops.push_back(op);
         *out = (tb_handle)c.denseops.size();
     });
@@ -1063,7 +1114,12 @@ int tb_denseop_destroy(tb_handle h) {
     return api([&] {
         DenseOp& op = get_op(h);
         spec_reset();
-        if (op.tmp_n) { cudaStreamSynchronize(ctx().stream); cudaFree(op.tmp_n); }
+        if (op.tmp_n || op.abs_rows || op.abs_cols) {
+            cudaStreamSynchronize(ctx().stream);
+            if (op.tmp_n) cudaFree(op.tmp_n);
+            if (op.abs_rows) cudaFree(op.abs_rows);
+            if (op.abs_cols) cudaFree(op.abs_cols);
+        }
         delete &op;
         ctx().denseops[(size_t)h - 1] = nullptr;
     });
