@@ -396,6 +396,7 @@ def main():
     ap.add_argument("--pair-fusion", type=int, default=1, help="serve op/trans_op pairs with one read of A when the backend can")
     ap.add_argument("--speculation", type=int, default=1, help="compute the next pair's products in the current read of A when its inputs are already final (csrc/gemv.cu)")
     ap.add_argument("--vprog", type=int, default=1, help="run the small vector commands between streaming launches as one launch per batch (csrc/vprog.cu)")
+    ap.add_argument("--scalar-prefetch", type=int, default=1, help="reductions that followed a host-visible scalar last time ride on its round trip (csrc/prefetch.cu)")
     ap.add_argument("--shim-protocol", type=int, default=0,
                     help="1: drive the backend with the Rust binding's call protocol (tb_view_of_host per operand, tb_buf_retain / "
                          "tb_buf_release per split child; totsu_b200/host/linalg.hpp) instead of carried (handle, offset, length) views")
@@ -456,6 +457,7 @@ def main():
     capi.check(L.tb_set_pair_fusion(1 if args.pair_fusion else 0))
     capi.check(L.tb_set_vprog(1 if args.vprog else 0))
     capi.check(L.tb_set_speculation(1 if args.speculation else 0))
+    capi.check(L.tb_set_scalar_prefetch(1 if args.scalar_prefetch else 0))
     host.set_shim_protocol(bool(args.shim_protocol))
     config["host_layer"] = ("C++ mirror of the unmodified Solver issuing the Rust binding's call protocol (tb_view_of_host per operand, retain / release per split child)"
                             if args.shim_protocol else "C++ mirror of the unmodified Solver carrying (handle, offset, length) views")
@@ -560,7 +562,9 @@ def main():
         capi.check(L.tb_vprog_stats(C.byref(vl), C.byref(vo)))
         sp = [C.c_uint64() for _ in range(3)]
         capi.check(L.tb_spec_stats(*[C.byref(v) for v in sp]))
-        return np.array([capi.launch_count(), vl.value, vo.value, sp[0].value, sp[1].value, sp[2].value], dtype=np.float64)
+        pf = [C.c_uint64() for _ in range(3)]
+        capi.check(L.tb_scalar_prefetch_stats(*[C.byref(v) for v in pf]))
+        return np.array([capi.launch_count(), vl.value, vo.value, sp[0].value, sp[1].value, sp[2].value, pf[0].value, pf[1].value, pf[2].value], dtype=np.float64)
 
     dev_precond = not qp_stock           # the fused route's calc_precond loops run as kernels (tb_recip_clamp); outside every timed window
     # ---- device-resident timing: R windows of EXACTLY K iterations, each bracketed by barrier + synchronize on both sides
@@ -711,6 +715,10 @@ def main():
             "vector_programs": {"enabled": bool(args.vprog), "launches_per_iteration": cnt[1] / steps,
                                 "micro_ops_per_iteration": cnt[2] / steps,
                                 "note": "small vector commands recorded into one cluster launch per batch (csrc/vprog.cu); each program counts as one of gpu_launches"},
+            "scalar_prefetch": {"enabled": bool(args.scalar_prefetch), "prefetch_kernels_per_iteration": cnt[6] / steps, "scalars_served_without_a_round_trip_per_iteration": cnt[7] / steps,
+                                "dropped": int(cnt[8]),
+                                "note": "g_x, g_y and |d| of criteria_conv (solver.rs:599-608) are computed behind the kappa / |p| round trips and served from the "
+                                        "mapped host box: 6 host round trips per iteration become 3"},
             "host": {"loop_s": win_host[med], "waiting_for_device_s": win_wait[med], "host_visible_scalars_per_iteration": win_scalars[med] / steps,
                      "note": "host time of the median window's loop and the part of it spent spinning on device results: the rest is issuing launches"},
             "clocks": clk, "last_residuals": [last.c0, last.c1, last.c2], "status_e2e": st}

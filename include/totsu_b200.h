@@ -81,9 +81,21 @@ int         tb_flush(void);
  * are bit-identical with it on or off.  tb_spec_stats: speculative passes launched / pairs served / speculations dropped. */
 int         tb_set_speculation(int on);
 int         tb_spec_stats(uint64_t* launched, uint64_t* served, uint64_t* dropped);
+/* Scalar prefetch (csrc/prefetch.cu): when a host-visible scalar has to be fetched from the device, the reductions that
+ * followed it last time (dot products into 1-element views, sums of squares: g_x, g_y, |p|, |d| of criteria_conv,
+ * solver.rs:599-608) are computed by one extra small kernel and ride on the same round trip; a device write overlapping their
+ * inputs drops them.  6 host round trips per solver iteration become 3.  Results agree with the un-prefetched path to rounding
+ * (double accumulation).  tb_scalar_prefetch_stats: prefetch kernels launched / requests served / prefetched values dropped. */
+int         tb_set_scalar_prefetch(int on);
+int         tb_scalar_prefetch_stats(uint64_t* launched, uint64_t* served, uint64_t* dropped);
 /* diagnostics: host seconds spent waiting for host-visible scalars (and how many waits) since the last call; a host that
  * never waits is launch-bound, one that mostly waits is device-bound */
 int         tb_host_wait_stats(double* seconds, uint64_t* waits);
+/* Tracing: every entry point of this header runs inside an NVTX range carrying its own name (nsys / ncu
+ * timelines; TB_NVTX=0 turns the ranges off).  tb_set_api_trace(1) additionally collects host-side call counts and wall
+ * seconds per entry point; tb_api_trace_dump writes "name calls seconds\n" lines into buf (needed = bytes required). */
+int         tb_set_api_trace(int on);
+int         tb_api_trace_dump(char* buf, size_t cap, size_t* needed);
 
 /* ---- buffers: the SliceLike role (slicelike.rs:23-69; totsu_f32cuda/src/f32cuda_slice.rs:215-309) ------- */
 /* SliceLike::new_ref / new_mut: wrap caller-owned host memory with a device mirror.  The host slice stays

@@ -202,5 +202,5 @@ def test_two_host_threads_share_the_backend():
         t.join()
     abuf.release()
     assert not errors, errors
-    for i in range(2):
-        assert np.array_equal(results[i][0], ref[0]) and np.array_equal(results[i][1], ref[1])
+    for i in range(2):      # interleaving changes which scalars ride on which round trip (prefetch.cu): equal to rounding, not bit for bit
+        assert np.allclose(results[i][0], ref[0], rtol=1e-5, atol=1e-7) and np.allclose(results[i][1], ref[1], rtol=1e-5, atol=1e-7)

@@ -145,7 +145,9 @@ def test_iterates_match_oracle(name, dt):
     # stated tolerances: relative l_inf of x_hat / y_hat vs the f64 oracle
     tol = {np.float64: {1: 1e-12, 10: 1e-11, 100: 1e-9}, np.float32: {1: 5e-6, 10: 5e-5, 100: 1e-4}}[dt]
     if name in ("sdp_like", "sdp_tc"):
-        tol = {k: v * (100 if dt == np.float32 else 1e4) for k, v in tol.items()}      # eigensolver conditioning
+        # SURVEY.md 8d / BASELINE.md: <= 1e-3 at K = 100 for the PSD configuration (C4) in f32; measured (profiles/r02_psd_iter_err.json,
+        # C4 itself at K = 100: 1.1e-5, profiles/r02_bench_c4_n1_parity100.json)
+        tol = {k: v * (10 if dt == np.float32 else 1e3) for k, v in tol.items()}
     abuf, av = H.device_matrix(a)
     results = {}
     for fused in (False, True):
@@ -447,3 +449,50 @@ def test_speculative_pairing_bit_identical_and_served(dt):
         abuf.release()
     assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1])
     assert out[1][2] == out[0][2]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name,fused", [("stream", True), ("socp", True), ("lp", False), ("wide", True)])
+def test_scalar_prefetch_halves_the_round_trips(name, fused, dt):
+    """csrc/prefetch.cu: g_x, g_y and |d| of criteria_conv (solver.rs:599-608) ride on the kappa / |p| round trips - the host
+    waits for the device 3 times per iteration instead of 6 - and the iterates agree with the un-prefetched run to rounding
+    (the prefetched reductions accumulate in double)."""
+    import ctypes as C
+    L = capi.lib()
+    blocks, n = (SYN[name] if name in SYN else WIDE[name])()
+    m = sum(l for _, l in blocks)
+    a, b, c = H.make_instance(m, n, blocks, seed=13, dtype=dt)
+    abuf, av = H.device_matrix(a)
+    out, waits, served = {}, {}, {}
+    iters = 40
+    try:
+        for on in (0, 1):
+            capi.check(L.tb_set_scalar_prefetch(on))
+            s = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=fused, fused_cone=fused)
+            assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=fused) == "None"
+            s.step(10)                  # learning iterations
+            hw_s, hw_n = C.c_double(), C.c_uint64()
+            capi.check(L.tb_host_wait_stats(C.byref(hw_s), C.byref(hw_n)))
+            pf0 = [C.c_uint64() for _ in range(3)]
+            capi.check(L.tb_scalar_prefetch_stats(*[C.byref(v) for v in pf0]))
+            s.step(iters)
+            capi.check(L.tb_host_wait_stats(C.byref(hw_s), C.byref(hw_n)))
+            pf1 = [C.c_uint64() for _ in range(3)]
+            capi.check(L.tb_scalar_prefetch_stats(*[C.byref(v) for v in pf1]))
+            waits[on] = hw_n.value / iters
+            served[on] = (pf1[1].value - pf0[1].value) / iters
+            assert pf1[2].value - pf0[2].value == 0 or not on          # steady state: nothing prefetched is thrown away
+            out[on] = s.xy() + ((s.last.c0, s.last.c1, s.last.c2),)
+            s.close()
+    finally:
+        capi.check(L.tb_set_scalar_prefetch(1))
+        abuf.release()
+    assert served[0] == 0 and served[1] == 3.0, served
+    if fused:                            # stock cones add their own host reads (ConeSOC: one scalar + one norm per block)
+        assert waits[0] == 6.0 and waits[1] == 3.0, waits
+    else:
+        assert waits[1] <= waits[0] - 3.0, waits
+    tol = 1e-11 if dt == np.float64 else 2e-5
+    assert H.rel_linf(out[1][0], out[0][0]) <= tol and H.rel_linf(out[1][1], out[0][1]) <= tol
+    for g, w in zip(out[1][2], out[0][2]):
+        assert abs(g - w) <= 50 * tol * max(abs(w), 1e-3)

@@ -57,6 +57,8 @@ def _signatures():
         "tb_host_wait_stats": (i, [C.POINTER(C.c_double), C.POINTER(u64)]),
         "tb_set_psd_pairing": (i, [i]), "tb_psd_pairs": (i, [C.POINTER(u64)]),
         "tb_set_speculation": (i, [i]), "tb_spec_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "tb_set_scalar_prefetch": (i, [i]), "tb_scalar_prefetch_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "tb_set_api_trace": (i, [i]), "tb_api_trace_dump": (i, [C.c_char_p, sz, C.POINTER(sz)]),
         "tb_set_vprog": (i, [i]), "tb_vprog_stats": (i, [C.POINTER(u64), C.POINTER(u64)]), "tb_flush": (i, []),
         "tb_prof_enable": (i, [i]), "tb_prof_read": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "tb_prof_read_variants": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -172,6 +174,19 @@ class Buf:
         out = np.empty(ln, dtype=self.dtype)
         check(lib().tb_download(self.view(off, ln), out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+def api_trace_table():
+    """{entry point: (calls, seconds)} collected since tb_set_api_trace(1)."""
+    need = C.c_size_t()
+    check(lib().tb_api_trace_dump(None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value + 16)
+    check(lib().tb_api_trace_dump(buf, len(buf), C.byref(need)))
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        name, calls, sec = ln.split()
+        out[name] = (int(calls), float(sec))
+    return out
 
 
 def stream_ptr():

@@ -233,8 +233,19 @@ extern bool g_cone_pending;
 void cone_flush_pending();
 
 // API wrapper: translate internal exceptions to status codes.
-template <typename F> inline int api_keep_pending(F f) {
+// Every C-ABI entry point runs inside an ApiScope: an NVTX range named after the entry point (visible in nsys / ncu
+// timelines; a no-op costing one predictable branch when no tool is attached and tracing is off) and, with
+// tb_set_api_trace(1), host-side call counts and wall time per entry point (tb_api_trace_dump).
+struct ApiScope {
+    const char* name;
+    bool on;
+    double t0;
+    explicit ApiScope(const char* n);
+    ~ApiScope();
+};
+template <typename F> inline int api_keep_pending_impl(const char* name, F f) {
     std::lock_guard<std::recursive_mutex> lock(api_mutex());
+    ApiScope scope(name);
     try {
         bind_thread();
         f();
@@ -247,8 +258,8 @@ template <typename F> inline int api_keep_pending(F f) {
         return TB_ERR_STATE;
     }
 }
-template <typename F> inline int api_raw(F f) {
-    return api_keep_pending([&] {
+template <typename F> inline int api_raw_impl(const char* name, F f) {
+    return api_keep_pending_impl(name, [&] {
         if (g_cone_pending) cone_flush_pending();
         f();
     });
@@ -256,16 +267,16 @@ template <typename F> inline int api_raw(F f) {
 void queue_drain();     // run every deferred command in program order (context.cu)
 // Default entry-point wrapper: anything deferred runs first, then the call itself - used by every function that
 // returns a value to the host, manages buffers, or is not worth deferring.
-template <typename F> inline int api(F f) {
-    return api_raw([&] {
+template <typename F> inline int api_impl(const char* name, F f) {
+    return api_raw_impl(name, [&] {
         if (!ctx().queue.empty()) queue_drain();
         f();
     });
 }
 // Deferrable entry point: runs at once unless a dense apply is parked, in which case it queues behind it.
 // `f` must capture its arguments by value.
-template <typename F> inline int api_defer(std::initializer_list<tb_view> reads, std::initializer_list<tb_view> writes, F f) {
-    return api_raw([&] {
+template <typename F> inline int api_defer_impl(const char* name, std::initializer_list<tb_view> reads, std::initializer_list<tb_view> writes, F f) {
+    return api_raw_impl(name, [&] {
         Context& c = ctx();
         if (c.queue.empty()) { f(); return; }
         Cmd cmd;
@@ -276,11 +287,25 @@ template <typename F> inline int api_defer(std::initializer_list<tb_view> reads,
         if (c.queue.size() > 16) queue_drain();
     });
 }
+// the entry points call these through macros so that the scope carries the entry point's own name
+#define api_keep_pending(...) ::tb::api_keep_pending_impl(__func__, __VA_ARGS__)
+#define api_raw(...) ::tb::api_raw_impl(__func__, __VA_ARGS__)
+#define api(...) ::tb::api_impl(__func__, __VA_ARGS__)
+#define api_defer(...) ::tb::api_defer_impl(__func__, __VA_ARGS__)
 bool cmds_conflict(const Cmd& a, const Cmd& b);
 // speculative pairing hooks (gemv.cu): every range that changes on the device, every buffer that goes away
 void spec_note_write(tb_handle buf, size_t off, size_t len);
 void spec_note_release(tb_handle buf);
 void spec_reset();
+// scalar prefetch hooks (prefetch.cu): reductions that followed a host-visible request last time ride on its round trip
+void pf_before_wait();
+void pf_note_write(tb_handle buf, size_t off, size_t len);
+void pf_note_release(tb_handle buf);
+void pf_reset();
+bool pf_try_dot(int dtype, const tb_view& a, const tb_view& x, const tb_view& y, double alpha, double beta, double* value_out);
+bool pf_try_sumsq(int dtype, const tb_view& a, double* value_out);
+void pf_miss_fetch(int dtype, const tb_view& elem);
+template <typename T> void set_scalar(const tb_view& one, T val);     // SliceLike::set on a 1-element view (context.cu)
 
 // ---- level-1 internals reused across translation units -------------------------------------------------
 template <typename T> void l1_scale(T alpha, T* x, size_t n);

@@ -7,6 +7,8 @@
 #include "vprog.cuh"
 #include <cstdlib>
 #include <chrono>
+#include <map>
+#include <nvtx3/nvToolsExt.h>
 
 namespace tb {
 
@@ -19,6 +21,27 @@ std::recursive_mutex& api_mutex() {
 }
 static thread_local std::string t_last_error;
 void set_last_error(const std::string& m) { t_last_error = m; }
+// ---- per-entry-point NVTX ranges + optional host-side call statistics (tb_set_api_trace / tb_api_trace_dump) ----
+static bool g_api_trace = false;
+static bool g_nvtx = true;                       // nvtx3 is header-only: calls are no-ops unless a tool injected itself
+struct ApiStat { uint64_t calls = 0; double seconds = 0.0; };
+static std::map<std::string, ApiStat> g_api_stats;
+static thread_local int t_api_depth = 0;
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+ApiScope::ApiScope(const char* n) : name(n), on(false), t0(0.0) {
+    if (t_api_depth++ > 0) return;               // nested scopes (deferred commands re-entering) belong to the outer call
+    if (g_nvtx) nvtxRangePushA(n);
+    if (g_api_trace) { on = true; t0 = now_s(); }
+}
+ApiScope::~ApiScope() {
+    if (--t_api_depth > 0) return;
+    if (on) {
+        ApiStat& st = g_api_stats[name];
+        st.calls += 1;
+        st.seconds += now_s() - t0;
+    }
+    if (g_nvtx) nvtxRangePop();
+}
 static thread_local int t_bound_device = -1;
 void bind_thread() {
     if (g_ctx.inited && t_bound_device != g_ctx.device) {
@@ -69,6 +92,7 @@ double box_wait(uint64_t seq) {
         Context& c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
         ~Timer() { c.box_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); c.box_waits += 1; }
     } timer{c};
+    pf_before_wait();        // reductions predicted to be asked for next are enqueued right behind the kernel being waited for
     for (unsigned long long spins = 0;; ++spins) {
         if (*flag == seq) break;
         if ((spins & 0xFFFF) == 0xFFFF) {
@@ -182,6 +206,7 @@ template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
         *out = reinterpret_cast<const T*>(b.host)[i];
         return;
     }
+    pf_miss_fetch(DT<T>::id, tb_view{v.buf, i, 1});
     if (vp_enabled()) {
         *out = (T)vp_fetch_to_host(DT<T>::id, b.dev + i * b.esize);      // last micro-op of the pending vector program
     } else {
@@ -213,6 +238,10 @@ template <typename T> static void set1(const tb_view& v, size_t idx, T val) {
         b.dev_newer.sub(v.off + idx, v.off + idx + 1);
     }
 }
+
+template <typename T> void set_scalar(const tb_view& one, T val) { set1<T>(one, 0, val); }
+template void set_scalar<float>(const tb_view&, float);
+template void set_scalar<double>(const tb_view&, double);
 
 }  // namespace tb
 
@@ -263,6 +292,7 @@ int tb_init(int device) {
         c.scratch_bytes = 0;
         (void)scratch(size_t(8) << 20);
         c.launches = 0;
+        if (const char* e = std::getenv("TB_NVTX")) g_nvtx = std::atoi(e) != 0;
         c.inited = true;
     });
 }
@@ -272,6 +302,7 @@ int tb_shutdown(void) {
         Context& c = ctx();
         if (!c.inited) return;
         c.queue.clear();
+        pf_reset();
         cudaStreamSynchronize(c.stream);
         for (Buffer& b : c.bufs)
             if (b.alive && b.small_slot < 0 && b.dev) cudaFree(b.dev);
@@ -356,6 +387,28 @@ int tb_host_wait_stats(double* seconds, uint64_t* waits) {
     return api_raw([&] {
         *seconds = ctx().box_wait_s; *waits = ctx().box_waits;
         ctx().box_wait_s = 0.0; ctx().box_waits = 0;
+    });
+}
+int tb_set_api_trace(int on) {
+    return api_keep_pending([&] {
+        g_api_trace = on != 0;
+        if (on) g_api_stats.clear();
+    });
+}
+int tb_api_trace_dump(char* buf, size_t cap, size_t* needed) {
+    return api_keep_pending([&] {
+        std::string out;
+        for (const auto& kv : g_api_stats) {
+            char line[256];
+            std::snprintf(line, sizeof line, "%s %llu %.9f\n", kv.first.c_str(), (unsigned long long)kv.second.calls, kv.second.seconds);
+            out += line;
+        }
+        if (needed) *needed = out.size() + 1;
+        if (buf && cap > 0) {
+            const size_t n = std::min(cap - 1, out.size());
+            std::memcpy(buf, out.data(), n);
+            buf[n] = 0;
+        }
     });
 }
 int tb_pairs_fused(uint64_t* out) {

@@ -670,6 +670,13 @@ static void api_transform_ge(int transpose, size_t n_row, size_t n_col, T alpha,
     } else {
         TB_REQUIRE(x.len == n_col && y.len == n_row, "transform_ge(N): vector length mismatch");   // :133-134
     }
+    if (transpose && n_col == 1 && n_row > 0) {      // MatOp n x 1 transposed (ProbLPOpC / OpB etc.): a dot product into a 1-element view
+        double v = 0.0;
+        if (pf_try_dot(DT<T>::id, mat, x, y, (double)alpha, (double)beta, &v)) {
+            set_scalar<T>(y, alpha * (T)v);
+            return;
+        }
+    }
     const T* A = rptr<T>(mat);
     const T* px = rptr<T>(x);
     T* py = wptr<T>(y, beta == T(0));
@@ -710,6 +717,13 @@ template <typename T> static void denseop_apply(tb_handle h, int transpose, T al
     const size_t m = op.n_row_total, n = op.n_col;
     if (transpose) TB_REQUIRE(x.len == m && y.len == n, "denseop trans_op: vector length mismatch");
     else TB_REQUIRE(x.len == n && y.len == m, "denseop op: vector length mismatch");
+    if (transpose && n == 1 && op.n_row == m) {      // an m x 1 operator transposed = a dot product into a 1-element view (c^T x, b^T y)
+        double v = 0.0;
+        if (pf_try_dot(DT<T>::id, op.mat, x, y, (double)alpha, (double)beta, &v)) {
+            set_scalar<T>(y, alpha * (T)v);          // served from the prefetched product: same arithmetic as the combine step it replaces
+            return;
+        }
+    }
     const T* A = rptr<T>(op.mat);
     const T* px = rptr<T>(x);
     T* py = wptr<T>(y, beta == T(0));
@@ -792,6 +806,7 @@ static inline bool view_overlaps(const tb_view& v, tb_handle buf, size_t off, si
 
 // called by dev_ptr for every range about to change on the device
 void spec_note_write(tb_handle buf, size_t off, size_t len) {
+    pf_note_write(buf, off, len);
     for (DenseOp* op : ctx().denseops)          // cached |A| sums die with any write into their matrix
         if (op != nullptr && op->abs_valid && view_overlaps(op->mat, buf, off, len)) op->abs_valid = false;
     SpecState& S = g_spec;
@@ -804,6 +819,7 @@ void spec_note_write(tb_handle buf, size_t off, size_t len) {
 }
 // a buffer went away: forget everything that names it (handles are recycled)
 void spec_note_release(tb_handle buf) {
+    pf_note_release(buf);
     SpecState& S = g_spec;
     auto names = [&](const SpecSig& g) { return g.xn.buf == buf || g.xt.buf == buf; };
     if (S.valid && names(S.sig)) S.valid = false;
