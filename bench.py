@@ -396,6 +396,7 @@ def main():
     ap.add_argument("--pair-fusion", type=int, default=1, help="serve op/trans_op pairs with one read of A when the backend can")
     ap.add_argument("--speculation", type=int, default=1, help="compute the next pair's products in the current read of A when its inputs are already final (csrc/gemv.cu)")
     ap.add_argument("--vprog", type=int, default=1, help="run the small vector commands between streaming launches as one launch per batch (csrc/vprog.cu)")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the small dependent kernels (csrc/common.cuh launch_pdl)")
     ap.add_argument("--scalar-prefetch", type=int, default=1, help="reductions that followed a host-visible scalar last time ride on its round trip (csrc/prefetch.cu)")
     ap.add_argument("--shim-protocol", type=int, default=0,
                     help="1: drive the backend with the Rust binding's call protocol (tb_view_of_host per operand, tb_buf_retain / "
@@ -458,6 +459,7 @@ def main():
     capi.check(L.tb_set_vprog(1 if args.vprog else 0))
     capi.check(L.tb_set_speculation(1 if args.speculation else 0))
     capi.check(L.tb_set_scalar_prefetch(1 if args.scalar_prefetch else 0))
+    capi.check(L.tb_set_pdl(1 if args.pdl else 0))
     host.set_shim_protocol(bool(args.shim_protocol))
     config["host_layer"] = ("C++ mirror of the unmodified Solver issuing the Rust binding's call protocol (tb_view_of_host per operand, retain / release per split child)"
                             if args.shim_protocol else "C++ mirror of the unmodified Solver carrying (handle, offset, length) views")
@@ -719,6 +721,7 @@ def main():
                                 "dropped": int(cnt[8]),
                                 "note": "g_x, g_y and |d| of criteria_conv (solver.rs:599-608) are computed behind the kappa / |p| round trips and served from the "
                                         "mapped host box: 6 host round trips per iteration become 3"},
+            "programmatic_dependent_launch": bool(args.pdl),
             "host": {"loop_s": win_host[med], "waiting_for_device_s": win_wait[med], "host_visible_scalars_per_iteration": win_scalars[med] / steps,
                      "note": "host time of the median window's loop and the part of it spent spinning on device results: the rest is issuing launches"},
             "clocks": clk, "last_residuals": [last.c0, last.c1, last.c2], "status_e2e": st}

@@ -59,6 +59,11 @@ int         tb_prof_read(uint64_t* launches, double* total_ms, double* total_byt
 /* the same records split by kernel variant: index NN * 3 + NT of stream_kernel<T, NN, NT> (NN / NT = number of A*x / A^T*x
  * products served by the one read of A: 3 = <1,0>, 1 = <0,1>, 4 = <1,1> pair, 8 = <2,2> pair + speculated pair); arrays of 9 */
 int         tb_prof_read_variants(uint64_t* launches9, double* ms9, double* bytes9);
+/* Programmatic dependent launch of the small dependent kernels of an iteration (vector programs, finalize, cone, peer
+ * exchange, reductions, the streaming kernel's prologue): the next kernel becomes resident while its predecessor runs and
+ * blocks in griddepcontrol.wait until it has completed - launch latency leaves the critical path.  Default on (TB_PDL=0 or
+ * tb_set_pdl(0): ordinary launches; results are identical either way). */
+int         tb_set_pdl(int on);
 /* tuning knob for tests: 0 = auto, 1 = force the generic (LDG) matvec, 2 = force the TMA matvec where legal */
 int         tb_set_gemv_path(int mode);
 /* Lazy op/trans_op pairing (default on): tb_denseop_apply parks the call until the opposite-direction apply on the
@@ -183,6 +188,14 @@ int tb_symm_gemm_trace_f32(size_t k, tb_view a, tb_view b, tb_view c, int splitk
 int tb_set_psd_pairing(int on);
 int tb_psd_pairs(uint64_t* out);
 int tb_proj_psd_f32(tb_view x, float eps_zero, tb_view work);
+/* MatBuild::set_sqrt (totsu/src/matbuild/mod.rs:220-241): mat := P^(1/2) for an upper-packed symmetric PSD P, i.e. map_eig with
+ * scale_diag = None and the closure e -> sqrt(e) on the positive eigenvalues - GEMM-only (coupled Newton-Schulz on the
+ * tcgen05 / FP64 engine of the ConePSD projection), with the Jacobi eigendecomposition as the fallback for k < 32 and for
+ * matrices the iteration cannot resolve.  tb_sqrt_psd_info: route of the last call (1 = Newton-Schulz, 2 = eigendecomposition)
+ * and its step count. */
+int tb_sqrt_psd_f32(tb_view mat, float eps_zero, tb_view work);
+int tb_sqrt_psd_f64(tb_view mat, double eps_zero, tb_view work);
+int tb_sqrt_psd_info(int* route, int* iterations);
 int tb_proj_psd_f64(tb_view x, double eps_zero, tb_view work);
 
 /* ---- fused device-resident Operator (operator.rs:11-156) for one stacked dense A ------------------------ */
@@ -238,6 +251,9 @@ int tb_dist_info(int* rank, int* world);
 /* 1 when the sharded operator's all-gather / all-reduce run as peer stores fused into the matvec epilogue
  * (cudaIpc-mapped staging over NVLink; TB_P2P=0 forces the NCCL baseline), 0 when they go through NCCL */
 int tb_dist_p2p_enabled(int* out);
+/* peer exchanges (one push + one wait kernel each) since tb_dist_init: a solver iteration needs 2 - the gather of A x and the
+ * reduce of A^T y of an op/trans_op pair travel together, and the speculated criteria_conv pair rides with the pair before it */
+int tb_dist_exchanges(uint64_t* out);
 
 #ifdef __cplusplus
 }

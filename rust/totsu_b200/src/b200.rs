@@ -59,6 +59,34 @@ impl<F: Elem> LinAlg for B200T<F> {
     }
 }
 
+enum Closure {
+    General,
+    KeepPositive,
+    Sqrt,
+}
+
+fn recognise<F: Elem, M: Fn(F) -> Option<F>>(map: &M) -> Closure {
+    const PROBES: [f64; 14] = [1e-30, 3e-21, 1e-12, 7e-7, 1e-3, 0.25, 1.0, 2.0, 9.0, 1234.5, 1e6, 3e12, 1e20, 1e30];
+    let (mut keep, mut root) = (true, true);
+    for pd in PROBES.iter() {
+        let e = F::from(*pd).unwrap();
+        match map(e) {
+            None => return Closure::General,
+            Some(out) => {
+                keep = keep && out == e;
+                root = root && out == e.sqrt();
+            }
+        }
+    }
+    if keep {
+        Closure::KeepPositive
+    } else if root {
+        Closure::Sqrt
+    } else {
+        Closure::General
+    }
+}
+
 impl<F: Elem> LinAlgEx for B200T<F> {
     fn transform_ge(transpose: bool, n_row: usize, n_col: usize, alpha: F, mat: &Self::Sl, x: &Self::Sl, beta: F, y: &mut Self::Sl) {
         assert_eq!(mat.len(), n_row * n_col);
@@ -89,6 +117,21 @@ impl<F: Elem> LinAlgEx for B200T<F> {
             Some(s) => (1, s),
             None => (0, F::one()),
         };
+        // The two closures the reference itself passes are recognised by probing them on positive arguments spanning the
+        // floating-point range (only eigenvalues > 0 ever reach the closure, f64lapack.rs:86-107) and served GEMM-only:
+        //   e -> Some(e)       ConePSD::proj (cone_psd.rs:69-76, scale_diag = Some(sqrt 2))  -> tb_proj_psd (matrix-sign iteration)
+        //   e -> Some(sqrt e)  MatBuild::set_sqrt (matbuild/mod.rs:231-238, scale_diag None) -> tb_sqrt_psd (coupled Newton-Schulz)
+        match recognise(&map) {
+            Closure::KeepPositive if scale_diag == Some((F::one() + F::one()).sqrt()) => {
+                check(unsafe { F::proj_psd(mat.view(), eps_zero, work.view()) }, "tb_proj_psd");
+                return;
+            }
+            Closure::Sqrt if scale_diag.is_none() => {
+                check(unsafe { F::sqrt_psd(mat.view(), eps_zero, work.view()) }, "tb_sqrt_psd");
+                return;
+            }
+            _ => {}
+        }
         // eigendecomposition on the device; only the n eigenvalues cross to the host for the closure
         let mut eigs = vec![F::zero(); n];
         check(

@@ -34,8 +34,10 @@ pub const TB_CONE_PSD: i32 = 4;
 
 macro_rules! typed_externs {
     ($F:ty, $get1:ident, $set1:ident, $norm:ident, $copy:ident, $scale:ident, $add:ident, $adds:ident, $abssum:ident, $di:ident,
-     $ge:ident, $sp:ident, $eb:ident, $ef:ident, $apply:ident, $acols:ident, $arows:ident, $proj:ident, $gmin:ident) => {
+     $ge:ident, $sp:ident, $eb:ident, $ef:ident, $apply:ident, $acols:ident, $arows:ident, $proj:ident, $gmin:ident, $ppsd:ident, $spsd:ident) => {
         extern "C" {
+            pub fn $ppsd(x: tb_view, eps_zero: $F, work: tb_view) -> c_int;
+            pub fn $spsd(mat: tb_view, eps_zero: $F, work: tb_view) -> c_int;
             pub fn $get1(v: tb_view, idx: usize, out: *mut $F) -> c_int;
             pub fn $set1(v: tb_view, idx: usize, val: $F) -> c_int;
             pub fn $norm(x: tb_view, out: *mut $F) -> c_int;
@@ -59,10 +61,10 @@ macro_rules! typed_externs {
 }
 typed_externs!(f32, tb_get1_f32, tb_set1_f32, tb_norm_f32, tb_copy_f32, tb_scale_f32, tb_add_f32, tb_adds_f32, tb_abssum_f32, tb_transform_di_f32,
                tb_transform_ge_f32, tb_transform_sp_f32, tb_map_eig_begin_f32, tb_map_eig_finish_f32, tb_denseop_apply_f32,
-               tb_denseop_absadd_cols_f32, tb_denseop_absadd_rows_f32, tb_cone_proj_f32, tb_cone_group_min_f32);
+               tb_denseop_absadd_cols_f32, tb_denseop_absadd_rows_f32, tb_cone_proj_f32, tb_cone_group_min_f32, tb_proj_psd_f32, tb_sqrt_psd_f32);
 typed_externs!(f64, tb_get1_f64, tb_set1_f64, tb_norm_f64, tb_copy_f64, tb_scale_f64, tb_add_f64, tb_adds_f64, tb_abssum_f64, tb_transform_di_f64,
                tb_transform_ge_f64, tb_transform_sp_f64, tb_map_eig_begin_f64, tb_map_eig_finish_f64, tb_denseop_apply_f64,
-               tb_denseop_absadd_cols_f64, tb_denseop_absadd_rows_f64, tb_cone_proj_f64, tb_cone_group_min_f64);
+               tb_denseop_absadd_cols_f64, tb_denseop_absadd_rows_f64, tb_cone_proj_f64, tb_cone_group_min_f64, tb_proj_psd_f64, tb_sqrt_psd_f64);
 
 extern "C" {
     pub fn tb_init(device: c_int) -> c_int;
@@ -112,12 +114,16 @@ pub trait Elem: num_traits::Float + Default + 'static {
     unsafe fn denseop_absadd_rows(op: tb_handle, sigma: tb_view) -> c_int;
     unsafe fn cone_proj(cone: tb_handle, dual_cone: c_int, x: tb_view, eps_zero: Self, psd_work: tb_view) -> c_int;
     unsafe fn cone_group_min(cone: tb_handle, dp_tau: tb_view) -> c_int;
+    unsafe fn proj_psd(x: tb_view, eps_zero: Self, work: tb_view) -> c_int;
+    unsafe fn sqrt_psd(mat: tb_view, eps_zero: Self, work: tb_view) -> c_int;
 }
 
 macro_rules! impl_elem {
     ($F:ty, $DT:expr, $get1:ident, $set1:ident, $norm:ident, $copy:ident, $scale:ident, $add:ident, $adds:ident, $abssum:ident, $di:ident,
-     $ge:ident, $sp:ident, $eb:ident, $ef:ident, $apply:ident, $acols:ident, $arows:ident, $proj:ident, $gmin:ident) => {
+     $ge:ident, $sp:ident, $eb:ident, $ef:ident, $apply:ident, $acols:ident, $arows:ident, $proj:ident, $gmin:ident, $ppsd:ident, $spsd:ident) => {
         impl Elem for $F {
+            unsafe fn proj_psd(x: tb_view, eps_zero: Self, work: tb_view) -> c_int { $ppsd(x, eps_zero, work) }
+            unsafe fn sqrt_psd(mat: tb_view, eps_zero: Self, work: tb_view) -> c_int { $spsd(mat, eps_zero, work) }
             const DTYPE: c_int = $DT;
             unsafe fn get1(v: tb_view, idx: usize, out: *mut Self) -> c_int { $get1(v, idx, out) }
             unsafe fn set1(v: tb_view, idx: usize, val: Self) -> c_int { $set1(v, idx, val) }
@@ -148,10 +154,10 @@ macro_rules! impl_elem {
 }
 impl_elem!(f32, TB_F32, tb_get1_f32, tb_set1_f32, tb_norm_f32, tb_copy_f32, tb_scale_f32, tb_add_f32, tb_adds_f32, tb_abssum_f32, tb_transform_di_f32,
            tb_transform_ge_f32, tb_transform_sp_f32, tb_map_eig_begin_f32, tb_map_eig_finish_f32, tb_denseop_apply_f32,
-           tb_denseop_absadd_cols_f32, tb_denseop_absadd_rows_f32, tb_cone_proj_f32, tb_cone_group_min_f32);
+           tb_denseop_absadd_cols_f32, tb_denseop_absadd_rows_f32, tb_cone_proj_f32, tb_cone_group_min_f32, tb_proj_psd_f32, tb_sqrt_psd_f32);
 impl_elem!(f64, TB_F64, tb_get1_f64, tb_set1_f64, tb_norm_f64, tb_copy_f64, tb_scale_f64, tb_add_f64, tb_adds_f64, tb_abssum_f64, tb_transform_di_f64,
            tb_transform_ge_f64, tb_transform_sp_f64, tb_map_eig_begin_f64, tb_map_eig_finish_f64, tb_denseop_apply_f64,
-           tb_denseop_absadd_cols_f64, tb_denseop_absadd_rows_f64, tb_cone_proj_f64, tb_cone_group_min_f64);
+           tb_denseop_absadd_cols_f64, tb_denseop_absadd_rows_f64, tb_cone_proj_f64, tb_cone_group_min_f64, tb_proj_psd_f64, tb_sqrt_psd_f64);
 
 /// The traits have no error channel, so a failed call panics - exactly like totsu_f32cuda asserts on every cuBLAS
 /// status (totsu_f32cuda/src/f32cuda.rs:38).

@@ -41,3 +41,19 @@ fn test_solver_fused_cone() {
     let rslt = s.solve((op_c, op_a, op_b, cone, &mut work)).unwrap();
     assert_float_eq!(rslt.0[0], -2., abs_all <= 1e-3);
 }
+
+// The f64 twin of the backend: same conformance problem, the reference's default eps_acc = 1e-6 converges in it.
+#[test]
+fn test_solver_f64() {
+    use totsu_b200::B200F64;
+    type Op<'a> = MatOp<'a, B200F64>;
+    let op_c = Op::new(MatType::General(1, 1), &[1.]);
+    let op_a = Op::new(MatType::General(3, 1), &[0., -1. * 1.41421356, -3.]);
+    let op_b = Op::new(MatType::General(3, 1), &[1., 0. * 1.41421356, 10.]);
+    let s = Solver::<B200F64>::new().par(|p| p.max_iter = Some(100_000));
+    let mut cone_w = vec![0.; ConePSD::<B200F64>::query_worklen(op_a.size().0)];
+    let cone = ConePSD::<B200F64>::new(&mut cone_w, s.par.eps_zero);
+    let mut work = vec![0.; Solver::<B200F64>::query_worklen(op_a.size())];
+    let rslt = s.solve((op_c, op_a, op_b, cone, &mut work)).unwrap();
+    assert_float_eq!(rslt.0[0], -2., abs_all <= 1e-3);
+}

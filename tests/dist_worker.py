@@ -99,6 +99,20 @@ def main():
                 tk = {np.float32: {1: 5e-6, 10: 5e-5, 50: 1e-4}, np.float64: {1: 1e-12, 10: 1e-11, 50: 1e-9}}[dt][k]
                 ex, ey = H.rel_linf(xh, snaps[k][0]), H.rel_linf(yh, snaps[k][1])
                 assert ex <= tk and ey <= tk, ("iterates", dt, m, n, k, ex, ey)
+            # replicas stay bit-identical through the solver loop (fixed summation order, same decisions on every rank)
+            mine = torch.from_numpy(np.concatenate([xh, yh]).astype(np.float64)).cuda()
+            ref = mine.clone(); dist.broadcast(ref, 0)
+            assert torch.equal(mine, ref), ("solver replicas diverged", dt, m, n)
+            if want_p2p and m_loc * n >= (1 << 20):
+                # steady state on a streaming-size shard: 2 peer exchanges per iteration (the speculated criteria_conv pair
+                # rides in the exchange of the pair before it), and every speculated pair is served
+                e0, e1 = C.c_uint64(), C.c_uint64()
+                sp0 = [C.c_uint64() for _ in range(3)]; sp1 = [C.c_uint64() for _ in range(3)]
+                capi.check(L.tb_dist_exchanges(C.byref(e0))); capi.check(L.tb_spec_stats(*[C.byref(v) for v in sp0]))
+                s.step(20)
+                capi.check(L.tb_dist_exchanges(C.byref(e1))); capi.check(L.tb_spec_stats(*[C.byref(v) for v in sp1]))
+                assert sp1[1].value - sp0[1].value == 20, ("speculated pairs served", sp1[1].value - sp0[1].value)
+                assert e1.value - e0.value == 2 * 20, ("peer exchanges per iteration", (e1.value - e0.value) / 20)
             s.close()
             abuf.release()
     capi.check(L.tb_device_sync())

@@ -165,6 +165,57 @@ def test_map_eig_sqrt_closure(dt, k):
     assert np.abs(packed - want).max() <= (2e-3 if dt == np.float32 else 1e-10) * max(1.0, np.abs(want).max())
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("k,kind", [(5, "full"), (40, "full"), (64, "full"), (256, "full"), (512, "full"), (512, "lowrank"), (512, "diag"), (2048, "full"), (96, "indefinite")])
+def test_sqrt_psd_vs_oracle(dt, k, kind):
+    """tb_sqrt_psd = MatBuild::set_sqrt (matbuild/mod.rs:220-241): map_eig(scale_diag = None, e -> sqrt(e)) of an upper-packed
+    symmetric PSD matrix, GEMM-only (coupled Newton-Schulz on the tcgen05 / FP64 engine) for k >= 32, against the oracle's
+    dsyevr route (f64lapack.rs:78-108).  k = 2048 is 2 orders of magnitude beyond what the Jacobi closure path could do in round 1;
+    `lowrank` (rank k/4) and `indefinite` exercise the fallback to the eigendecomposition."""
+    if k >= 2048 and dt == np.float64:
+        pytest.skip("f64 at k = 2048 runs on the FP64 pipe: minutes")
+    rng = np.random.default_rng(k + len(kind))
+    if kind == "full":
+        g = rng.standard_normal((k, k + 8))
+        p = g @ g.T / k + 0.05 * np.eye(k)
+    elif kind == "lowrank":
+        g = rng.standard_normal((k, k // 4))
+        p = g @ g.T / k
+    elif kind == "diag":
+        p = np.diag(rng.uniform(0.05, 1.0, k))                      # bench.py's C2 P
+    else:
+        g = rng.standard_normal((k, k))
+        p = (g + g.T) / 2                                           # not PSD: the closure drops the negative eigenvalues
+    p = p.astype(dt).astype(np.float64)
+    packed = np.array([p[r, c] for c in range(k) for r in range(c + 1)], dtype=dt) if k <= 512 else p.T[np.tril_indices(k)].astype(dt)
+    w, v = np.linalg.eigh(p)
+    want_m = (v * np.sqrt(np.maximum(w, 0.0))) @ v.T                  # same as dsyevr(V, (0, inf]) + dsyr with sqrt(e)
+    if k <= 64:
+        want_o = packed.astype(np.float64).copy()
+        O.F64LAPACK.map_eig(want_o, None, 1e-12, np.zeros(O.F64LAPACK.map_eig_worklen(k)), lambda e: math.sqrt(e) if e > 0 else None)
+        assert np.abs(want_o - want_m.T[np.tril_indices(k)]).max() <= 1e-9 * np.abs(want_m).max()
+    mb, wb = capi.Buf(packed), capi.Buf(dtype=dt, length=2 * k * k + k)
+    capi.check(capi.fn("tb_sqrt_psd", dt)(mb.view(), 1e-12, wb.view()))
+    route, iters = C.c_int(), C.c_int()
+    capi.check(capi.lib().tb_sqrt_psd_info(C.byref(route), C.byref(iters)))
+    mb.release(); wb.release()
+    got = np.zeros((k, k))
+    got.T[np.tril_indices(k)] = packed
+    got = np.triu(got) + np.triu(got, 1).T
+    if kind in ("full", "diag") and k >= 32:
+        assert route.value == 1 and 3 <= iters.value <= 40, (route.value, iters.value)      # the GEMM-only route took it
+    if kind == "indefinite":
+        assert route.value == 2
+    scale = np.abs(want_m).max()
+    # sqrt is ill-conditioned at 0: compare S (to sqrt of the working precision for rank-deficient P) and S^2 = P+ (tight)
+    tol_s = {"full": 3e-5, "diag": 3e-5, "lowrank": 3e-3, "indefinite": 3e-3}[kind] if dt == np.float32 else \
+            {"full": 1e-11, "diag": 1e-11, "lowrank": 1e-6, "indefinite": 1e-8}[kind]
+    assert np.abs(got - want_m).max() <= tol_s * scale, (np.abs(got - want_m).max() / scale, route.value, iters.value)
+    p_plus = (v * np.maximum(w, 0.0)) @ v.T
+    tol_p = 1e-4 if dt == np.float32 else 1e-10
+    assert np.abs(got @ got - p_plus).max() <= tol_p * np.abs(p_plus).max()
+
+
 def _spectrum_matrix(k, lam, seed):
     rng = np.random.default_rng(seed)
     q, _ = np.linalg.qr(rng.standard_normal((k, k)))

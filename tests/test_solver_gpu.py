@@ -144,10 +144,9 @@ def test_iterates_match_oracle(name, dt):
     snaps, trace = H.oracle_iterates(a, b, c, blocks, ks)
     # stated tolerances: relative l_inf of x_hat / y_hat vs the f64 oracle
     tol = {np.float64: {1: 1e-12, 10: 1e-11, 100: 1e-9}, np.float32: {1: 5e-6, 10: 5e-5, 100: 1e-4}}[dt]
-    if name in ("sdp_like", "sdp_tc"):
-        # SURVEY.md 8d / BASELINE.md: <= 1e-3 at K = 100 for the PSD configuration (C4) in f32; measured (profiles/r02_psd_iter_err.json,
-        # C4 itself at K = 100: 1.1e-5, profiles/r02_bench_c4_n1_parity100.json)
-        tol = {k: v * (10 if dt == np.float32 else 1e3) for k, v in tol.items()}
+    # The PSD instances get NO looser tolerance (round 1 multiplied by 100 / 1e4): measured with scripts/psd_iter_err.py on B200,
+    # K = 100: f32 8e-7 (fused) .. 1.8e-5 (stock, k = 64), f64 1.8e-12; C4 itself (k = 512, f32) 1.1e-5 at K = 100
+    # (profiles/r02_bench_c4_n1_parity100.json) - two orders of magnitude inside the 1e-3 that SURVEY.md 8d allows for C4.
     abuf, av = H.device_matrix(a)
     results = {}
     for fused in (False, True):
@@ -164,8 +163,6 @@ def test_iterates_match_oracle(name, dt):
             it = s.last
             ref = trace[k - 1]
             rt = 5e-3 if dt == np.float32 else 1e-8
-            if name in ("sdp_like", "sdp_tc"):
-                rt *= 20
             for got, want in zip((it.c0, it.c1, it.c2), ref[1:]):
                 if not np.isfinite(want):          # criteria_inf branch: inf when m_cx / m_by <= eps_zero (solver.rs:640-653)
                     assert (np.isinf(want) and got == want) or np.isnan(want), (name, dt, fused, k, got, want)
@@ -496,3 +493,29 @@ def test_scalar_prefetch_halves_the_round_trips(name, fused, dt):
     assert H.rel_linf(out[1][0], out[0][0]) <= tol and H.rel_linf(out[1][1], out[0][1]) <= tol
     for g, w in zip(out[1][2], out[0][2]):
         assert abs(g - w) <= 50 * tol * max(abs(w), 1e-3)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("name", ["stream", "socp", "sdp_tc", "wide"])
+def test_programmatic_dependent_launch_changes_nothing(name, dt):
+    """The hot-loop kernels are launched with programmatic stream serialization (common.cuh launch_pdl): each may become
+    resident while its predecessor still runs and waits in griddepcontrol.wait before touching memory.  With it on or off
+    the iterates and residuals are bit-identical."""
+    L = capi.lib()
+    blocks, n = (SYN[name] if name in SYN else WIDE[name])()
+    m = sum(l for _, l in blocks)
+    a, b, c = H.make_instance(m, n, blocks, seed=21, dtype=dt)
+    abuf, av = H.device_matrix(a)
+    out = {}
+    try:
+        for on in (1, 0):
+            capi.check(L.tb_set_pdl(on))
+            s = host.Session.dense(dt, av, m, n, c, b, blocks, fused_op=True, fused_cone=True)
+            assert s.begin(max_iter=None, eps_acc=0.0, eps_inf=0.0, device_precond=True) == "None"
+            s.step(60)
+            out[on] = s.xy() + ((s.last.c0, s.last.c1, s.last.c2),)
+            s.close()
+    finally:
+        capi.check(L.tb_set_pdl(1))
+        abuf.release()
+    assert np.array_equal(out[1][0], out[0][0]) and np.array_equal(out[1][1], out[0][1]) and out[1][2] == out[0][2]

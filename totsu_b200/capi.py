@@ -52,7 +52,7 @@ def _signatures():
     sig = {
         "tb_init": (i, [i]), "tb_shutdown": (i, []), "tb_last_error": (C.c_char_p, []), "tb_device_sync": (i, []),
         "tb_get_stream": (i, [C.POINTER(vp)]), "tb_sm_count": (i, [C.POINTER(i)]),
-        "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_psd_path": (i, [i]),
+        "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_pdl": (i, [i]), "tb_set_psd_path": (i, [i]),
         "tb_set_pair_fusion": (i, [i]), "tb_pairs_fused": (i, [C.POINTER(u64)]),
         "tb_host_wait_stats": (i, [C.POINTER(C.c_double), C.POINTER(u64)]),
         "tb_set_psd_pairing": (i, [i]), "tb_psd_pairs": (i, [C.POINTER(u64)]),
@@ -67,12 +67,13 @@ def _signatures():
         "tb_host_ref": (i, [View]), "tb_host_mut": (i, [View]),
         "tb_upload": (i, [View, vp]), "tb_download": (i, [View, vp]),
         "tb_map_eig_worklen": (sz, [sz]),
+        "tb_sqrt_psd_info": (i, [C.POINTER(i), C.POINTER(i)]),
         "tb_symm_gemm_f32": (i, [sz, C.c_float, View, View, C.c_float, View, C.c_float, View, i, i]),
         "tb_symm_gemm_trace_f32": (i, [sz, View, View, View, i, i, C.POINTER(u64)]),
         "tb_denseop_create": (i, [i, View, sz, sz, sz, sz, C.POINTER(H)]), "tb_denseop_destroy": (i, [H]),
         "tb_cone_create": (i, [C.POINTER(ConeBlock), sz, C.POINTER(H)]), "tb_cone_destroy": (i, [H]),
         "tb_dist_unique_id": (i, [vp]), "tb_dist_init": (i, [i, i, vp]), "tb_dist_finalize": (i, []),
-        "tb_dist_info": (i, [C.POINTER(i), C.POINTER(i)]), "tb_dist_p2p_enabled": (i, [C.POINTER(i)]),
+        "tb_dist_info": (i, [C.POINTER(i), C.POINTER(i)]), "tb_dist_p2p_enabled": (i, [C.POINTER(i)]), "tb_dist_exchanges": (i, [C.POINTER(u64)]),
     }
     for dt, F in _F.items():
         s = _SUF[dt]
@@ -86,7 +87,7 @@ def _signatures():
             f"tb_transform_sp_{s}": (i, [sz, F, View, View, F, View]),
             f"tb_map_eig_begin_{s}": (i, [View, i, F, F, View, FP]),
             f"tb_map_eig_finish_{s}": (i, [View, i, F, View, FP, C.POINTER(C.c_uint8)]),
-            f"tb_proj_psd_{s}": (i, [View, F, View]),
+            f"tb_proj_psd_{s}": (i, [View, F, View]), f"tb_sqrt_psd_{s}": (i, [View, F, View]),
             f"tb_denseop_apply_{s}": (i, [H, i, F, View, F, View]),
             f"tb_denseop_apply_pair_{s}": (i, [H, F, View, F, View, F, View, F, View]),
             f"tb_denseop_absadd_cols_{s}": (i, [H, View]), f"tb_denseop_absadd_rows_{s}": (i, [H, View]),
@@ -180,12 +181,13 @@ def api_trace_table():
     """{entry point: (calls, seconds)} collected since tb_set_api_trace(1)."""
     need = C.c_size_t()
     check(lib().tb_api_trace_dump(None, 0, C.byref(need)))
-    buf = C.create_string_buffer(need.value + 16)
+    buf = C.create_string_buffer(need.value + 4096)       # the dump call itself is traced: leave room for its own line
     check(lib().tb_api_trace_dump(buf, len(buf), C.byref(need)))
     out = {}
     for ln in buf.value.decode().splitlines():
-        name, calls, sec = ln.split()
-        out[name] = (int(calls), float(sec))
+        f = ln.split()
+        if len(f) == 3:
+            out[f[0]] = (int(f[1]), float(f[2]))
     return out
 
 

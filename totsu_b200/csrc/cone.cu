@@ -96,6 +96,7 @@ __device__ __forceinline__ void soc_block(T* x, unsigned long long len, int type
 template <typename T, int MODE>
 __global__ void __launch_bounds__(CN_THREADS) cone_kernel(T* x, const ConeItem* __restrict__ items, const SmallBlock* __restrict__ small, int dual_cone) {
     __shared__ double red[32];
+    tbd::pdl_entry();
     const ConeItem it = items[blockIdx.x];
     if (it.kind == 0) {
         if (MODE == 1) return;                                 // Zero / RPos: product_group does nothing
@@ -212,7 +213,7 @@ template <typename T> static void cone_proj(tb_handle h, int dual_cone, tb_view 
     T* px = wptr<T>(x);
     Context& c = ctx();
     if (cs.has_work) {
-        cone_kernel<T, 0><<<cs.n_items, CN_THREADS, 0, c.stream>>>(px, cs.d_items, cs.d_small, dual_cone);
+        launch_pdl(cone_kernel<T, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, dual_cone);
         TB_LAUNCH_CHECK();
     }
     if (cs.has_psd) {
@@ -260,9 +261,9 @@ static void cone_proj_pair(const PendingProj& p0, tb_handle h, int dual1, tb_vie
     float* px1 = wptr<float>(x1);
     float* pw = wptr<float>(w);
     if (cs.has_work) {
-        cone_kernel<float, 0><<<cs.n_items, CN_THREADS, 0, c.stream>>>(px0, cs.d_items, cs.d_small, p0.dual);
+        launch_pdl(cone_kernel<float, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px0, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, p0.dual);
         TB_LAUNCH_CHECK();
-        cone_kernel<float, 0><<<cs.n_items, CN_THREADS, 0, c.stream>>>(px1, cs.d_items, cs.d_small, dual1);
+        launch_pdl(cone_kernel<float, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px1, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, dual1);
         TB_LAUNCH_CHECK();
     }
     size_t off = 0;

@@ -42,6 +42,14 @@ ApiScope::~ApiScope() {
     }
     if (g_nvtx) nvtxRangePop();
 }
+static int g_pdl = -1;
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = std::getenv("TB_PDL");
+        g_pdl = (e && std::atoi(e) == 0) ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
 static thread_local int t_bound_device = -1;
 void bind_thread() {
     if (g_ctx.inited && t_bound_device != g_ctx.device) {
@@ -123,6 +131,7 @@ void* scratch(size_t bytes) {
 // (a cudaMemcpyAsync from pageable memory may synchronise the stream).
 struct SmallPayload { unsigned char b[Context::kSmallBytes]; };
 __global__ void poke_kernel(unsigned char* dst, SmallPayload p, unsigned int nbytes) {
+    tbd::pdl_entry();
     for (unsigned int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = p.b[i];
 }
 
@@ -140,7 +149,7 @@ char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite) {
                 if (nb <= Context::kSmallBytes) {
                     SmallPayload p;
                     std::memcpy(p.b, b.host + lo * b.esize, nb);
-                    poke_kernel<<<1, 64, 0, c.stream>>>((unsigned char*)(b.dev + lo * b.esize), p, (unsigned int)nb);
+                    launch_pdl(poke_kernel, dim3(1), dim3(64), 0, c.stream, (unsigned char*)(b.dev + lo * b.esize), p, (unsigned int)nb);
                     TB_LAUNCH_CHECK();
                 } else {
                     TB_CUDA(cudaMemcpyAsync(b.dev + lo * b.esize, b.host + lo * b.esize, nb, cudaMemcpyHostToDevice, c.stream));
@@ -192,8 +201,8 @@ static void host_sync_range(Buffer& b, size_t off, size_t len) {
     }
 }
 
-template <typename T> __global__ void set1_kernel(T* p, T v) { *p = v; }
-template <typename T> __global__ void fetch1_kernel(const T* p, double* box, unsigned long long seq) { tbd::box_post(box, (double)*p, seq); }
+template <typename T> __global__ void set1_kernel(T* p, T v) { tbd::pdl_entry(); *p = v; }
+template <typename T> __global__ void fetch1_kernel(const T* p, double* box, unsigned long long seq) { tbd::pdl_entry(); tbd::box_post(box, (double)*p, seq); }
 
 template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
     require_init();
@@ -211,7 +220,7 @@ template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
         *out = (T)vp_fetch_to_host(DT<T>::id, b.dev + i * b.esize);      // last micro-op of the pending vector program
     } else {
         const uint64_t seq = box_next();
-        fetch1_kernel<T><<<1, 1, 0, c.stream>>>(reinterpret_cast<const T*>(b.dev + i * b.esize), c.hostbox_dev, seq);
+        launch_pdl(fetch1_kernel<T>, dim3(1), dim3(1), 0, c.stream, reinterpret_cast<const T*>(b.dev + i * b.esize), c.hostbox_dev, (unsigned long long)seq);
         TB_LAUNCH_CHECK();
         *out = (T)box_wait(seq);            // T -> double -> T is exact
     }
@@ -229,7 +238,7 @@ template <typename T> static void set1(const tb_view& v, size_t idx, T val) {
     if (vp_enabled()) {
         vp_set1(DT<T>::id, p, (double)val);
     } else {
-        set1_kernel<T><<<1, 1, 0, ctx().stream>>>(p, val);
+        launch_pdl(set1_kernel<T>, dim3(1), dim3(1), 0, ctx().stream, p, val);
         TB_LAUNCH_CHECK();
     }
     Buffer& b = get_buf(v.buf);
@@ -413,6 +422,13 @@ int tb_api_trace_dump(char* buf, size_t cap, size_t* needed) {
 }
 int tb_pairs_fused(uint64_t* out) {
     return api([&] { *out = ctx().pairs_fused; });
+}
+
+int tb_set_pdl(int on) {
+    return api([&] {
+        if (ctx().inited) TB_CUDA(cudaStreamSynchronize(ctx().stream));
+        g_pdl = on != 0 ? 1 : 0;
+    });
 }
 
 int tb_set_gemv_path(int mode) {

@@ -84,6 +84,7 @@ struct PeerExchange {
     int* fault_dev = nullptr;
     void* tmp = nullptr;            // NCCL-path staging for all-reduce partials
     size_t tmp_bytes = 0;
+    uint64_t exchanges = 0;         // peer exchanges (push + wait) since tb_dist_init
 };
 static PeerExchange g_px;
 
@@ -111,6 +112,7 @@ template <typename T, int MODE, bool FROM_PARTS>
 __global__ void __launch_bounds__(256) peer_push_kernel(const PeerPtrs pp, uint64_t seq, const T* __restrict__ src, int nparts, size_t ld, size_t len,
                                                         T alpha, T beta, T* y_local, size_t stage_off, unsigned int* ticket) {
     __shared__ bool last;
+    tbd::pdl_entry();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
         T v;
         if (FROM_PARTS) {
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const PeerPtrs pp, uint6
 // MODE 0: y[r*count + i] = stage[r*count + i] for r != rank;  MODE 1: y[i] = alpha * sum_r stage[r*count + i] + beta*y[i]
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) peer_wait_kernel(const PeerPtrs pp, uint64_t seq, size_t count, T alpha, T beta, T* y, int* fault) {
+    tbd::pdl_entry();
     if (threadIdx.x < pp.world && (MODE == 1 || (int)threadIdx.x != pp.rank)) {
         const uint64_t* flag = reinterpret_cast<const uint64_t*>(pp.region[pp.rank]) + threadIdx.x;
         if (ld_acquire_sys(flag) < seq) {
@@ -177,31 +180,55 @@ __global__ void __launch_bounds__(256) peer_wait_kernel(const PeerPtrs pp, uint6
 }
 
 // Both collectives of one op/trans_op pair in ONE exchange: the push kernel finalizes my slice of A x (alpha/beta applied,
-// stored into my y and every peer's stage) AND stores my partial of A^T x into every rank's stage behind the gather area
-// (stage layout: [world * len_g gathered slices | world * len_r reduce partials]), then releases one flag per peer; the
-// wait kernel acquires the flags once, copies the gathered slices and sums the reduce partials in rank order.  Halves the
-// launches and the flag round trips of a pair (6 exchanges per solver iteration -> 3).
+// stored into my y and every peer's stage) AND stores my partial of A^T x into every rank's stage behind the gather area,
+// then releases one flag per peer; the wait kernel acquires the flags once, copies the gathered slices and sums the reduce
+// partials in rank order.  Halves the launches and the flag round trips of a pair (6 exchanges per solver iteration -> 3).
+//
+// A SECOND, speculated pair can ride in the same exchange (len_g2 / len_r2 > 0): the raw products of the pair that will be
+// asked for next (gemv.cu "speculative pairing": its alpha, beta and output views are not known yet) are summed per rank,
+// pushed behind the first pair's areas and left - gathered / reduced in rank order, un-scaled - in local buffers, so that
+// when the pair arrives it is served by a local axpby: 3 exchanges per solver iteration -> 2.
+// Stage layout: [world*len_g gathered | world*len_r partials | world*len_g2 raw gathered | world*len_r2 raw partials].
+template <typename T> struct PairSeg {
+    const T* part_g; int nparts_g; size_t ld_g, len_g; T alpha_g, beta_g; T* y_local;     // gather of the carrying pair
+    const T* part_r; int nparts_r; size_t ld_r, len_r;                                    // reduce of the carrying pair
+    const T* part_g2; int nparts_g2; size_t ld_g2, len_g2;                                // speculated pair: raw gather
+    const T* part_r2; int nparts_r2; size_t ld_r2, len_r2;                                // speculated pair: raw reduce
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256) peer_push_pair_kernel(const PeerPtrs pp, uint64_t seq,
-                                                             const T* __restrict__ part_g, int nparts_g, size_t ld_g, size_t len_g, T alpha_g, T beta_g, T* y_local,
-                                                             const T* __restrict__ part_r, int nparts_r, size_t ld_r, size_t len_r, unsigned int* ticket) {
+__global__ void __launch_bounds__(256) peer_push_pair_kernel(const PeerPtrs pp, uint64_t seq, const PairSeg<T> g, unsigned int* ticket) {
     __shared__ bool last;
-    const size_t goff = (size_t)pp.rank * len_g;
-    const size_t rbase = (size_t)pp.world * len_g;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len_g + len_r; i += (size_t)gridDim.x * blockDim.x) {
-        if (i < len_g) {
+    tbd::pdl_entry();
+    const size_t goff = (size_t)pp.rank * g.len_g;
+    const size_t rbase = (size_t)pp.world * g.len_g;
+    const size_t g2base = rbase + (size_t)pp.world * g.len_r;
+    const size_t r2base = g2base + (size_t)pp.world * g.len_g2;
+    const size_t e1 = g.len_g, e2 = e1 + g.len_r, e3 = e2 + g.len_g2, e4 = e3 + g.len_r2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < e4; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < e1) {
             T s = T(0);
-            for (int j = 0; j < nparts_g; ++j) s += part_g[(size_t)j * ld_g + i];
-            T v = alpha_g * s;
-            if (beta_g != T(0)) v += beta_g * y_local[i];
-            y_local[i] = v;
+            for (int j = 0; j < g.nparts_g; ++j) s += g.part_g[(size_t)j * g.ld_g + i];
+            T v = g.alpha_g * s;
+            if (g.beta_g != T(0)) v += g.beta_g * g.y_local[i];
+            g.y_local[i] = v;
             for (int p = 0; p < pp.world; ++p)
                 if (p != pp.rank) stage_ptr<T>(pp, p, seq)[goff + i] = v;
-        } else {
-            const size_t k = i - len_g;
+        } else if (i < e2) {
+            const size_t k = i - e1;
             T s = T(0);
-            for (int j = 0; j < nparts_r; ++j) s += part_r[(size_t)j * ld_r + k];
-            for (int p = 0; p < pp.world; ++p) stage_ptr<T>(pp, p, seq)[rbase + (size_t)pp.rank * len_r + k] = s;
+            for (int j = 0; j < g.nparts_r; ++j) s += g.part_r[(size_t)j * g.ld_r + k];
+            for (int p = 0; p < pp.world; ++p) stage_ptr<T>(pp, p, seq)[rbase + (size_t)pp.rank * g.len_r + k] = s;
+        } else if (i < e3) {
+            const size_t k = i - e2;
+            T s = T(0);
+            for (int j = 0; j < g.nparts_g2; ++j) s += g.part_g2[(size_t)j * g.ld_g2 + k];
+            for (int p = 0; p < pp.world; ++p) stage_ptr<T>(pp, p, seq)[g2base + (size_t)pp.rank * g.len_g2 + k] = s;
+        } else {
+            const size_t k = i - e3;
+            T s = T(0);
+            for (int j = 0; j < g.nparts_r2; ++j) s += g.part_r2[(size_t)j * g.ld_r2 + k];
+            for (int p = 0; p < pp.world; ++p) stage_ptr<T>(pp, p, seq)[r2base + (size_t)pp.rank * g.len_r2 + k] = s;
         }
     }
     __threadfence_system();
@@ -220,7 +247,9 @@ __global__ void __launch_bounds__(256) peer_push_pair_kernel(const PeerPtrs pp, 
 
 template <typename T>
 __global__ void __launch_bounds__(256) peer_wait_pair_kernel(const PeerPtrs pp, uint64_t seq, size_t len_g, T* y_g_base,
-                                                             size_t len_r, T alpha_r, T beta_r, T* y_r, int* fault) {
+                                                             size_t len_r, T alpha_r, T beta_r, T* y_r,
+                                                             size_t len_g2, T* raw_g2, size_t len_r2, T* raw_r2, int* fault) {
+    tbd::pdl_entry();
     if (threadIdx.x < pp.world) {
         const uint64_t* flag = reinterpret_cast<const uint64_t*>(pp.region[pp.rank]) + threadIdx.x;
         if (ld_acquire_sys(flag) < seq) {
@@ -234,16 +263,29 @@ __global__ void __launch_bounds__(256) peer_wait_pair_kernel(const PeerPtrs pp, 
     const T* st = stage_ptr<T>(pp, pp.rank, seq);
     const size_t total_g = len_g * (size_t)pp.world;
     const size_t lo = len_g * (size_t)pp.rank, hi = lo + len_g;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_g + len_r; i += (size_t)gridDim.x * blockDim.x) {
-        if (i < total_g) {
+    const size_t rbase = total_g;
+    const size_t g2base = rbase + (size_t)pp.world * len_r;
+    const size_t total_g2 = len_g2 * (size_t)pp.world;
+    const size_t r2base = g2base + total_g2;
+    const size_t e1 = total_g, e2 = e1 + len_r, e3 = e2 + total_g2, e4 = e3 + len_r2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < e4; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < e1) {
             if (i < lo || i >= hi) y_g_base[i] = __ldcg(st + i);
-        } else {
-            const size_t k = i - total_g;
+        } else if (i < e2) {
+            const size_t k = i - e1;
             T s = T(0);
-            for (int r = 0; r < pp.world; ++r) s += __ldcg(st + total_g + (size_t)r * len_r + k);
+            for (int r = 0; r < pp.world; ++r) s += __ldcg(st + rbase + (size_t)r * len_r + k);
             T v = alpha_r * s;
             if (beta_r != T(0)) v += beta_r * y_r[k];
             y_r[k] = v;
+        } else if (i < e3) {
+            const size_t k = i - e2;
+            raw_g2[k] = __ldcg(st + g2base + k);
+        } else {
+            const size_t k = i - e3;
+            T s = T(0);
+            for (int r = 0; r < pp.world; ++r) s += __ldcg(st + r2base + (size_t)r * len_r2 + k);
+            raw_r2[k] = s;
         }
     }
 }
@@ -272,26 +314,28 @@ template <typename T> static bool px_fits(size_t elems) { return g_px.on && elem
 template <typename T> static void px_gather(const T* src, bool from_parts, int nparts, size_t ld, size_t len_local, T alpha, T beta, T* y_base) {
     Context& c = ctx();
     const uint64_t seq = ++g_px.seq;
+    g_px.exchanges += 1;
     T* y_local = y_base + (size_t)c.rank * len_local;
     const size_t off = (size_t)c.rank * len_local;
     if (from_parts)
-        peer_push_kernel<T, 0, true><<<px_grid(len_local), 256, 0, c.stream>>>(g_px.pp, seq, src, nparts, ld, len_local, alpha, beta, y_local, off, px_ticket());
+        launch_pdl(peer_push_kernel<T, 0, true>, dim3(px_grid(len_local)), dim3(256), 0, c.stream, g_px.pp, seq, src, nparts, ld, len_local, alpha, beta, y_local, off, px_ticket());
     else
-        peer_push_kernel<T, 0, false><<<px_grid(len_local), 256, 0, c.stream>>>(g_px.pp, seq, src, 0, 0, len_local, T(1), T(0), y_local, off, px_ticket());
+        launch_pdl(peer_push_kernel<T, 0, false>, dim3(px_grid(len_local)), dim3(256), 0, c.stream, g_px.pp, seq, src, 0, (size_t)0, len_local, T(1), T(0), y_local, off, px_ticket());
     TB_LAUNCH_CHECK();
-    peer_wait_kernel<T, 0><<<px_grid(len_local * c.world), 256, 0, c.stream>>>(g_px.pp, seq, len_local, T(1), T(0), y_base, g_px.fault_dev);
+    launch_pdl(peer_wait_kernel<T, 0>, dim3(px_grid(len_local * c.world)), dim3(256), 0, c.stream, g_px.pp, seq, len_local, T(1), T(0), y_base, g_px.fault_dev);
     TB_LAUNCH_CHECK();
 }
 
 template <typename T> static void px_reduce(const T* src, bool from_parts, int nparts, size_t ld, size_t n, T alpha, T beta, T* y) {
     Context& c = ctx();
     const uint64_t seq = ++g_px.seq;
+    g_px.exchanges += 1;
     if (from_parts)
-        peer_push_kernel<T, 1, true><<<px_grid(n), 256, 0, c.stream>>>(g_px.pp, seq, src, nparts, ld, n, T(1), T(0), nullptr, 0, px_ticket());
+        launch_pdl(peer_push_kernel<T, 1, true>, dim3(px_grid(n)), dim3(256), 0, c.stream, g_px.pp, seq, src, nparts, ld, n, T(1), T(0), (T*)nullptr, (size_t)0, px_ticket());
     else
-        peer_push_kernel<T, 1, false><<<px_grid(n), 256, 0, c.stream>>>(g_px.pp, seq, src, 0, 0, n, T(1), T(0), nullptr, 0, px_ticket());
+        launch_pdl(peer_push_kernel<T, 1, false>, dim3(px_grid(n)), dim3(256), 0, c.stream, g_px.pp, seq, src, 0, (size_t)0, n, T(1), T(0), (T*)nullptr, (size_t)0, px_ticket());
     TB_LAUNCH_CHECK();
-    peer_wait_kernel<T, 1><<<px_grid(n), 256, 0, c.stream>>>(g_px.pp, seq, n, alpha, beta, y, g_px.fault_dev);
+    launch_pdl(peer_wait_kernel<T, 1>, dim3(px_grid(n)), dim3(256), 0, c.stream, g_px.pp, seq, n, alpha, beta, y, g_px.fault_dev);
     TB_LAUNCH_CHECK();
 }
 
@@ -339,17 +383,50 @@ void dist_finalize_pair(const T* part_n, int nparts_n, size_t ld_n, size_t len_l
     static const bool fused = [] { const char* e = getenv("TB_P2P_PAIR"); return !(e && e[0] == '0'); }();
     if (fused && c.world > 1 && len_local > 0 && n > 0 && px_fits<T>((len_local + n) * (size_t)c.world)) {
         const uint64_t seq = ++g_px.seq;
+    g_px.exchanges += 1;
         T* y_local = y_base + (size_t)c.rank * len_local;
-        peer_push_pair_kernel<T><<<px_grid(len_local + n), 256, 0, c.stream>>>(g_px.pp, seq, part_n, nparts_n, ld_n, len_local, alpha_n, beta_n, y_local,
-                                                                            part_t, nparts_t, ld_t, n, px_ticket());
+        PairSeg<T> g{part_n, nparts_n, ld_n, len_local, alpha_n, beta_n, y_local, part_t, nparts_t, ld_t, n, nullptr, 0, 0, 0, nullptr, 0, 0, 0};
+        launch_pdl(peer_push_pair_kernel<T>, dim3(px_grid(len_local + n)), dim3(256), 0, c.stream, g_px.pp, seq, g, px_ticket());
         TB_LAUNCH_CHECK();
-        peer_wait_pair_kernel<T><<<px_grid(len_local * c.world + n), 256, 0, c.stream>>>(g_px.pp, seq, len_local, y_base, n, alpha_t, beta_t, y_t, g_px.fault_dev);
+        launch_pdl(peer_wait_pair_kernel<T>, dim3(px_grid(len_local * c.world + n)), dim3(256), 0, c.stream, g_px.pp, seq, len_local, y_base, n, alpha_t, beta_t, y_t,
+                   (size_t)0, (T*)nullptr, (size_t)0, (T*)nullptr, g_px.fault_dev);
         TB_LAUNCH_CHECK();
         return;
     }
     dist_finalize_gather<T>(part_n, nparts_n, ld_n, len_local, alpha_n, beta_n, y_base);
     dist_finalize_reduce<T>(part_t, nparts_t, ld_t, n, alpha_t, beta_t, y_t);
 }
+// The carrying pair's epilogues AND the speculated pair's raw products in ONE exchange (see PairSeg).  raw_n (world*len_local)
+// and raw_t (n) receive the speculated pair's gathered / reduced sums, un-scaled.  Returns false - nothing done - when the peer
+// path cannot take it (NCCL baseline, stage too small, TB_P2P_SPEC=0): the caller then finalizes the carrying pair on its own
+// and exchanges the speculated one when it is asked for.
+template <typename T>
+bool dist_finalize_pair_spec(const T* part_n, int nparts_n, size_t ld_n, size_t len_local, T alpha_n, T beta_n, T* y_base,
+                             const T* part_t, int nparts_t, size_t ld_t, size_t n, T alpha_t, T beta_t, T* y_t,
+                             const T* spec_n, const T* spec_t, T* raw_n, T* raw_t) {
+    Context& c = ctx();
+    static const bool on = [] {
+        const char* e = getenv("TB_P2P_SPEC");
+        const char* f = getenv("TB_P2P_PAIR");
+        return !(e && e[0] == '0') && !(f && f[0] == '0');
+    }();
+    if (!on || c.world <= 1 || len_local == 0 || n == 0 || !px_fits<T>(2 * (len_local + n) * (size_t)c.world)) return false;
+    const uint64_t seq = ++g_px.seq;
+    g_px.exchanges += 1;
+    T* y_local = y_base + (size_t)c.rank * len_local;
+    PairSeg<T> g{part_n, nparts_n, ld_n, len_local, alpha_n, beta_n, y_local, part_t, nparts_t, ld_t, n,
+                 spec_n, nparts_n, ld_n, len_local, spec_t, nparts_t, ld_t, n};
+    launch_pdl(peer_push_pair_kernel<T>, dim3(px_grid(2 * (len_local + n))), dim3(256), 0, c.stream, g_px.pp, seq, g, px_ticket());
+    TB_LAUNCH_CHECK();
+    launch_pdl(peer_wait_pair_kernel<T>, dim3(px_grid(2 * (len_local * c.world + n))), dim3(256), 0, c.stream, g_px.pp, seq, len_local, y_base, n, alpha_t, beta_t, y_t,
+               len_local, raw_n, n, raw_t, g_px.fault_dev);
+    TB_LAUNCH_CHECK();
+    return true;
+}
+template bool dist_finalize_pair_spec<float>(const float*, int, size_t, size_t, float, float, float*, const float*, int, size_t, size_t, float, float, float*,
+                                             const float*, const float*, float*, float*);
+template bool dist_finalize_pair_spec<double>(const double*, int, size_t, size_t, double, double, double*, const double*, int, size_t, size_t, double, double, double*,
+                                              const double*, const double*, double*, double*);
 template void dist_finalize_pair<float>(const float*, int, size_t, size_t, float, float, float*, const float*, int, size_t, size_t, float, float, float*);
 template void dist_finalize_pair<double>(const double*, int, size_t, size_t, double, double, double*, const double*, int, size_t, size_t, double, double, double*);
 template void dist_finalize_gather<float>(const float*, int, size_t, size_t, float, float, float*);
@@ -522,6 +599,10 @@ int tb_dist_finalize(void) {
 
 int tb_dist_p2p_enabled(int* out) {
     return api([&] { *out = g_px.on ? 1 : 0; });
+}
+
+int tb_dist_exchanges(uint64_t* out) {
+    return api_raw([&] { *out = g_px.exchanges; });
 }
 
 int tb_dist_info(int* rank, int* world) {

@@ -509,6 +509,104 @@ static void api_map_eig_finish(tb_view mat, int has_scale, T scale_diag, tb_view
     eig_reconstruct<T>(x, k, has_scale != 0, scale_diag, a, w, z);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// MatBuild::set_sqrt at real size (totsu/src/matbuild/mod.rs:220-241: map_eig with the closure e -> sqrt(e), called once
+// per ProbQP / ProbQCQP construction, qp.rs:386, qcqp.rs:445-448): P^(1/2) of a symmetric PSD matrix WITHOUT an
+// eigendecomposition - the coupled Newton-Schulz iteration, three symmetric GEMMs per step on the same engine as the
+// ConePSD projection (tcgen05 3xTF32 for f32, FP64 pipe for f64):
+//     Y0 = P / ||P||_F,  Z0 = I;     R = I - Z Y;   Y <- Y + Y R / 2;   Z <- Z + Z R / 2;      Y -> (P/||P||_F)^(1/2)
+// (all iterates are polynomials in P: symmetric and commuting, so the symmetric-operand GEMM applies).  ||R||_F is read
+// back after every step - one 8-byte round trip next to three k^3 GEMMs - and the loop ends when it is at rounding level
+// or has stopped shrinking.  Returns false (matrix untouched) if the iteration does not converge - P indefinite or
+// numerically singular beyond what the working precision resolves - so that the caller can take the Jacobi route.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> __global__ void identity_kernel(T* __restrict__ a, size_t k) {
+    size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= k * k) return;
+    a[idx] = (idx % k == idx / k) ? T(1) : T(0);
+}
+template <typename T> __global__ void scale_sqrt_norm_kernel(T* __restrict__ y, size_t n, const double* __restrict__ sumsq) {
+    const T f = (T)sqrt(sqrt(*sumsq));          // sqrt(||P||_F)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] *= f;
+}
+
+template <typename T> static bool psd_sqrt_newton_schulz(T* x, size_t k, int* iters_out) {
+    Context& c = ctx();
+    const size_t kk = k * k;
+    T* sc = reinterpret_cast<T*>(eig_scratch(6 * kk * sizeof(T)));
+    T* X = sc; T* Y = sc + kk; T* Z = sc + 2 * kk; T* R = sc + 3 * kk; T* Yn = sc + 4 * kk; T* Zn = sc + 5 * kk;
+    double* sumsq = c.mailbox_dev + 20;
+    double* rsq = c.mailbox_dev + 21;
+    const unsigned gkk = (unsigned)((kk + 255) / 256);
+    unpack_kernel<T><<<gkk, 256, 0, c.stream>>>(x, k, 0, T(1), X);
+    TB_LAUNCH_CHECK();
+    l1_sumsq_async<T>(X, kk, sumsq);
+    scale_inv_norm_kernel<T><<<std::min<unsigned>(gkk, 4096u), 256, 0, c.stream>>>(X, Y, kk, sumsq);
+    TB_LAUNCH_CHECK();
+    identity_kernel<T><<<gkk, 256, 0, c.stream>>>(Z, k);
+    TB_LAUNCH_CHECK();
+    double nrm2 = 0.0;
+    TB_CUDA(cudaMemcpyAsync(&nrm2, sumsq, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    TB_CUDA(cudaStreamSynchronize(c.stream));
+    if (!(nrm2 > 0.0)) { if (iters_out) *iters_out = 0; return std::isfinite(nrm2); }      // the zero matrix is its own square root
+    const double floor_r = (sizeof(T) == 4 ? 2e-6 : 1e-14) * (double)k;        // ||R||_F at rounding level: ~eps * sqrt(k) per entry, k^2 entries
+    const int max_it = 100;
+    double r_prev = 1e300;
+    bool ok = false;
+    int it = 0;
+    for (; it < max_it; ++it) {
+        symm_gemm<T>(Z, Y, nullptr, R, k, T(-1), T(0), T(1));                  // R = I - Z Y
+        l1_sumsq_async<T>(R, kk, rsq);
+        double r2 = 0.0;
+        TB_CUDA(cudaMemcpyAsync(&r2, rsq, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        symm_gemm<T>(Y, R, Y, Yn, k, T(0.5), T(1), T(0));                      // Y' = Y + Y R / 2   (enqueued while the host waits for r)
+        symm_gemm<T>(Z, R, Z, Zn, k, T(0.5), T(1), T(0));                      // Z' = Z + Z R / 2
+        TB_CUDA(cudaStreamSynchronize(c.stream));
+        const double r = sqrt(r2);
+        if (!std::isfinite(r) || r > 4.0 * (double)k) break;                   // diverging: not PSD
+        std::swap(Y, Yn); std::swap(Z, Zn);
+        if (r <= floor_r || (r_prev < 0.25 && r > 0.5 * r_prev)) { ok = true; ++it; break; }
+        r_prev = r;
+    }
+    if (iters_out) *iters_out = it;
+    if (!ok) return false;
+    scale_sqrt_norm_kernel<T><<<std::min<unsigned>(gkk, 4096u), 256, 0, c.stream>>>(Y, kk, sumsq);
+    TB_LAUNCH_CHECK();
+    pack_kernel<T><<<gkk, 256, 0, c.stream>>>(Y, k, 0, T(1), x);
+    TB_LAUNCH_CHECK();
+    return true;
+}
+
+static int g_last_sqrt_iters = 0, g_last_sqrt_route = 0;     // diagnostics: tb_sqrt_psd_info
+
+// map_eig(mat, None, eps_zero, work, |e| if e > 0 { Some(sqrt(e)) } else { None }) - exactly MatBuild::set_sqrt's call
+template <typename T> static void api_sqrt_psd(tb_view mat, T eps_zero, tb_view work) {
+    require_init();
+    const size_t k = tri_dim(mat.len);
+    TB_REQUIRE(k * (k + 1) / 2 == mat.len, "sqrt_psd: length is not a triangular number");
+    TB_REQUIRE(work.len >= 2 * k * k + k, "sqrt_psd: work shortage");                      // matbuild/mod.rs:226-229
+    if (k == 0) return;
+    T* x = wptr<T>(mat);
+    g_last_sqrt_route = 0;
+    if (k >= 32 && ctx().psd_mode != 1 && psd_sqrt_newton_schulz<T>(x, k, &g_last_sqrt_iters)) {
+        g_last_sqrt_route = 1;
+        return;
+    }
+    // small matrices and anything the GEMM-only iteration cannot resolve: eigendecomposition, sqrt of the positive eigenvalues
+    T* wk = wptr<T>(work);
+    T* a = wk; T* w = wk + k * k; T* z = w + k;
+    eig_decompose<T>(x, k, false, T(1), a, w, z);
+    std::vector<T> ev(k);
+    TB_CUDA(cudaMemcpyAsync(ev.data(), w, k * sizeof(T), cudaMemcpyDeviceToHost, ctx().stream));
+    TB_CUDA(cudaStreamSynchronize(ctx().stream));
+    for (size_t i = 0; i < k; ++i) ev[i] = ev[i] > T(0) ? (T)std::sqrt(ev[i]) : T(0);
+    (void)eps_zero;
+    TB_CUDA(cudaMemcpyAsync(w, ev.data(), k * sizeof(T), cudaMemcpyHostToDevice, ctx().stream));
+    TB_CUDA(cudaStreamSynchronize(ctx().stream));
+    eig_reconstruct<T>(x, k, false, T(1), a, w, z);
+    g_last_sqrt_route = 2;
+}
+
 template <typename T> static void api_proj_psd(tb_view x, T eps_zero, tb_view work) {
     require_init();
     T* px = wptr<T>(x);
@@ -559,6 +657,11 @@ int tb_symm_gemm_trace_f32(size_t k, tb_view a, tb_view b, tb_view cv, int split
         TB_CUDA(cudaStreamSynchronize(ctx().stream));
         TB_CUDA(cudaFree(dev));
     });
+}
+int tb_sqrt_psd_f32(tb_view m, float ez, tb_view w) { return api([&] { api_sqrt_psd<float>(m, ez, w); }); }
+int tb_sqrt_psd_f64(tb_view m, double ez, tb_view w) { return api([&] { api_sqrt_psd<double>(m, ez, w); }); }
+int tb_sqrt_psd_info(int* route, int* iterations) {
+    return api_raw([&] { *route = g_last_sqrt_route; *iterations = g_last_sqrt_iters; });
 }
 int tb_proj_psd_f32(tb_view x, float ez, tb_view w) { return api([&] { api_proj_psd<float>(x, ez, w); }); }
 int tb_proj_psd_f64(tb_view x, double ez, tb_view w) { return api([&] { api_proj_psd<double>(x, ez, w); }); }

@@ -32,6 +32,7 @@ namespace tb {
 // -------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void finalize_kernel(const T* __restrict__ part, int nparts, size_t ld, size_t len, T alpha, T beta, T* y) {
+    tbd::pdl_entry();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
         T s = T(0);
         for (int j = 0; j < nparts; ++j) s += part[(size_t)j * ld + i];
@@ -45,7 +46,7 @@ template <typename T> void l2_finalize(const T* part, int nparts, size_t ld, siz
     if (len == 0) return;
     if (vp_enabled_wide(len)) { vp_finalize(DT<T>::id, part, nparts, ld, len, (double)alpha, (double)beta, y); return; }
     int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
-    finalize_kernel<T><<<g, 256, 0, ctx().stream>>>(part, nparts, ld, len, alpha, beta, y);
+    launch_pdl(finalize_kernel<T>, dim3(g), dim3(256), 0, ctx().stream, part, nparts, ld, len, alpha, beta, y);
     TB_LAUNCH_CHECK();
 }
 template void l2_finalize<float>(const float*, int, size_t, size_t, float, float, float*);
@@ -58,6 +59,7 @@ template <typename T> static void finalize(const T* part, int nparts, size_t ld,
 template <typename T>
 __global__ void finalize2_kernel(const T* __restrict__ part_a, int nparts_a, size_t ld_a, size_t len_a, T alpha_a, T beta_a, T* y_a,
                                  const T* __restrict__ part_b, int nparts_b, size_t ld_b, size_t len_b, T alpha_b, T beta_b, T* y_b) {
+    tbd::pdl_entry();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len_a + len_b; i += (size_t)gridDim.x * blockDim.x) {
         const bool first = i < len_a;
         const T* part = first ? part_a : part_b;
@@ -84,7 +86,7 @@ static void finalize2(const T* part_a, int nparts_a, size_t ld_a, size_t len_a, 
         return;
     }
     int g = (int)std::min<size_t>((len + 255) / 256, (size_t)ctx().sm_count * 8);
-    finalize2_kernel<T><<<g, 256, 0, ctx().stream>>>(part_a, nparts_a, ld_a, len_a, alpha_a, beta_a, y_a, part_b, nparts_b, ld_b, len_b, alpha_b, beta_b, y_b);
+    launch_pdl(finalize2_kernel<T>, dim3(g), dim3(256), 0, ctx().stream, part_a, nparts_a, ld_a, len_a, alpha_a, beta_a, y_a, part_b, nparts_b, ld_b, len_b, alpha_b, beta_b, y_b);
     TB_LAUNCH_CHECK();
 }
 
@@ -96,6 +98,7 @@ template <typename T, bool ABS>
 __global__ void gemv_n_generic(const T* __restrict__ A, size_t lda, size_t n_row, size_t n_col,
                                const T* __restrict__ x, T* __restrict__ out, size_t ld_out, size_t cols_per_split,
                                bool direct, T alpha, T beta) {
+    tbd::pdl_entry();
     size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t c0 = (size_t)blockIdx.y * cols_per_split;
     size_t c1 = c0 + cols_per_split < n_col ? c0 + cols_per_split : n_col;
@@ -133,6 +136,7 @@ __global__ void gemv_t_generic(const T* __restrict__ A, size_t lda, size_t n_row
     constexpr int CW = 8;
     __shared__ T red[CW][8];
     __shared__ bool last;
+    tbd::pdl_entry();
     size_t cb = (size_t)blockIdx.x * CW;
     size_t r0 = (size_t)blockIdx.y * rows_per_split;
     size_t r1 = r0 + rows_per_split < n_row ? r0 + rows_per_split : n_row;
@@ -220,11 +224,11 @@ static void run_generic_n(const T* A, size_t lda, size_t n_row, size_t n_col, co
     splits = n_col == 0 ? 1 : (n_col + cps - 1) / cps;
     dim3 grid((unsigned)row_blocks, (unsigned)splits);
     if (splits == 1) {
-        gemv_n_generic<T, ABS><<<grid, 128, 0, c.stream>>>(A, lda, n_row, n_col, x, y, 0, std::max<size_t>(cps, 1), true, alpha, beta);
+        launch_pdl(gemv_n_generic<T, ABS>, grid, dim3(128), 0, c.stream, A, lda, n_row, n_col, x, y, (size_t)0, std::max<size_t>(cps, 1), true, alpha, beta);
         TB_LAUNCH_CHECK();
     } else {
         T* part = reinterpret_cast<T*>(scratch(splits * n_row * sizeof(T)));
-        gemv_n_generic<T, ABS><<<grid, 128, 0, c.stream>>>(A, lda, n_row, n_col, x, part, n_row, cps, false, alpha, beta);
+        launch_pdl(gemv_n_generic<T, ABS>, grid, dim3(128), 0, c.stream, A, lda, n_row, n_col, x, part, n_row, cps, false, alpha, beta);
         TB_LAUNCH_CHECK();
         finalize<T>(part, (int)splits, n_row, n_row, alpha, beta, y);
     }
@@ -248,13 +252,13 @@ static void run_generic_t(const T* A, size_t lda, size_t n_row, size_t n_col, co
     TB_REQUIRE(col_groups <= 2147483647u, "too many columns");
     dim3 grid((unsigned)col_groups, (unsigned)splits);
     if (splits == 1) {
-        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, y, 0, std::max<size_t>(rps, 1), true, alpha, beta, nullptr, nullptr);
+        launch_pdl(gemv_t_generic<T, ABS>, grid, dim3(256), 0, c.stream, A, lda, n_row, n_col, x, y, (size_t)0, std::max<size_t>(rps, 1), true, alpha, beta, (T*)nullptr, (unsigned int*)nullptr);
         TB_LAUNCH_CHECK();
     } else {
         T* part = reinterpret_cast<T*>(scratch(splits * n_col * sizeof(T)));
         const bool fused = col_groups <= (size_t)Context::kTicketPool;      // one ticket per column group
-        gemv_t_generic<T, ABS><<<grid, 256, 0, c.stream>>>(A, lda, n_row, n_col, x, part, n_col, rps, false, alpha, beta,
-                                                           fused ? y : nullptr, c.tickets + 64);
+        launch_pdl(gemv_t_generic<T, ABS>, grid, dim3(256), 0, c.stream, A, lda, n_row, n_col, x, part, n_col, rps, false, alpha, beta,
+                   fused ? y : (T*)nullptr, c.tickets + 64);
         TB_LAUNCH_CHECK();
         if (!fused) finalize<T>(part, (int)splits, n_col, n_col, alpha, beta, y);
     }
@@ -329,6 +333,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) stream_kernel(const StreamP
         }
         ptx::mbar_fence_init();
     }
+    tbd::pdl_entry();          // barrier set-up above overlaps the tail of the previous kernel; no global access before this point
     __syncthreads();
 
     // contiguous range of work units for this CTA; unit u = chunk * n_splits + split
@@ -533,7 +538,7 @@ template <typename T, int NN, int NT, bool ABS = false> static void launch_strea
         e0 = get_ev(); e1 = get_ev();
         TB_CUDA(cudaEventRecord(e0, c.stream));
     }
-    stream_kernel<T, NN, NT, ABS><<<grid, kStreamThreads, smem, c.stream>>>(p);
+    launch_pdl(stream_kernel<T, NN, NT, ABS>, dim3(grid), dim3(kStreamThreads), smem, c.stream, p);
     TB_LAUNCH_CHECK();
     if (c.prof_on) {
         TB_CUDA(cudaEventRecord(e1, c.stream));
@@ -554,6 +559,12 @@ template <typename T> struct SpecJob {
     T* part_n;            // out: [n_splits][n_row], allocated by run_stream
     T* part_t;            // out: [n_chunks][n_col]
     size_t n_splits, n_chunks;
+    // sharded: when the speculated pair's raw products travelled in the carrying pair's exchange (dist.cu PairSeg) they are
+    // already gathered / reduced over the ranks, un-scaled: raw_n [world * n_row], raw_t [n_col]
+    size_t n_row_total;   // in: rows of the whole operator
+    T* raw_n;
+    T* raw_t;
+    bool exchanged;
 };
 char* spec_buffer(size_t bytes);
 
@@ -618,13 +629,26 @@ static void run_stream(const T* A, size_t lda, size_t n_row, size_t n_col,
         // second N pass and second T pass on the same staged tiles: their partials outlive this call in the spec buffer
         size_t sb_n = n_splits * n_row * sizeof(T);
         sb_n = (sb_n + 255) & ~size_t(255);
-        char* sb = spec_buffer(sb_n + n_chunks * n_col * sizeof(T));
+        size_t sb_t = n_chunks * n_col * sizeof(T);
+        sb_t = (sb_t + 255) & ~size_t(255);
+        size_t sb_rn = sharded ? spec->n_row_total * sizeof(T) : 0;
+        sb_rn = (sb_rn + 255) & ~size_t(255);
+        char* sb = spec_buffer(sb_n + sb_t + sb_rn + (sharded ? n_col * sizeof(T) : 0));
         spec->part_n = reinterpret_cast<T*>(sb);
         spec->part_t = reinterpret_cast<T*>(sb + sb_n);
+        spec->raw_n = reinterpret_cast<T*>(sb + sb_n + sb_t);
+        spec->raw_t = reinterpret_cast<T*>(sb + sb_n + sb_t + sb_rn);
+        spec->exchanged = false;
         spec->n_splits = n_splits; spec->n_chunks = n_chunks;
         p.x_n[1] = spec->x_n; p.x_t[1] = spec->x_t;
         p.part_n[1] = spec->part_n; p.part_t[1] = spec->part_t;
         launch_stream<T, 2, 2>(p, grid, smem);
+        if (sharded && dist_finalize_pair_spec<T>(reinterpret_cast<const T*>(p.part_n[0]), (int)n_splits, n_row, n_row, alpha_n, beta_n, y_n,
+                                                  reinterpret_cast<const T*>(p.part_t[0]), (int)n_chunks, n_col, n_col, alpha_t, beta_t, y_t,
+                                                  spec->part_n, spec->part_t, spec->raw_n, spec->raw_t)) {
+            spec->exchanged = true;       // one exchange carried both pairs: the speculated one will be served by a local axpby
+            return;
+        }
     } else if (abs_ones) {
         TB_REQUIRE(do_n && do_t, "internal: the |A| pass produces both sums");
         launch_stream<T, 1, 1, true>(p, grid, smem);
@@ -779,6 +803,9 @@ struct SpecState {
     void* part_n = nullptr;
     void* part_t = nullptr;
     size_t n_splits = 0, n_chunks = 0;
+    void* raw_n = nullptr;      // sharded + exchanged: gathered / reduced raw products (see SpecJob)
+    void* raw_t = nullptr;
+    bool exchanged = false;
     char* buf = nullptr;
     size_t buf_bytes = 0;
     bool have_last = false;
@@ -859,8 +886,14 @@ static void denseop_apply_pair(tb_handle h, T alpha_n, tb_view x_n, T beta_n, tb
         T* syn = wptr<T>(y_n, beta_n == T(0));
         T* syt = wptr<T>(y_t, beta_t == T(0));
         if (S.valid) {                                   // the output views may overlap the inputs: wptr above would have dropped it
-            stream_finalize_partials<T>(reinterpret_cast<const T*>(S.part_n), S.n_splits, reinterpret_cast<const T*>(S.part_t), S.n_chunks,
-                                        op.n_row, n, alpha_n, beta_n, syn, alpha_t, beta_t, syt, sharded);
+            if (S.exchanged) {
+                // the raw products crossed the ranks with the carrying pair: only alpha / beta are left to apply, locally
+                l1_axpby<T>(alpha_n, reinterpret_cast<const T*>(S.raw_n), beta_n, syn, m);
+                l1_axpby<T>(alpha_t, reinterpret_cast<const T*>(S.raw_t), beta_t, syt, n);
+            } else {
+                stream_finalize_partials<T>(reinterpret_cast<const T*>(S.part_n), S.n_splits, reinterpret_cast<const T*>(S.part_t), S.n_chunks,
+                                            op.n_row, n, alpha_n, beta_n, syn, alpha_t, beta_t, syt, sharded);
+            }
             S.valid = false;
             c.spec_served += 1;
             if (S.have_last && S.last_op == h) {
@@ -901,6 +934,7 @@ static void denseop_apply_pair(tb_handle h, T alpha_n, tb_view x_n, T beta_n, tb
         nsig = *next;                                    // copy: the table may be edited below
         job.x_n = rptr<T>(nsig.xn);
         job.x_t = rptr<T>(nsig.xt);
+        job.n_row_total = m;
         if (sharded) job.x_t += op.row_offset;
     }
     T* pyn = wptr<T>(y_n, beta_n == T(0));
@@ -926,6 +960,7 @@ static void denseop_apply_pair(tb_handle h, T alpha_n, tb_view x_n, T beta_n, tb
     if (spec_ok && streams) {
         S.valid = true; S.op = h; S.dtype = DT<T>::id; S.sig = nsig;
         S.part_n = job.part_n; S.part_t = job.part_t; S.n_splits = job.n_splits; S.n_chunks = job.n_chunks;
+        S.raw_n = job.raw_n; S.raw_t = job.raw_t; S.exchanged = job.exchanged;
         c.spec_launched += 1;
     }
 }

@@ -63,6 +63,7 @@ __global__ void reduce_kernel(const T* __restrict__ x, size_t count, size_t inc,
                               double* box, unsigned long long seq) {
     __shared__ double red[32];
     __shared__ bool last;
+    tbd::pdl_entry();
     double acc = 0.0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
         double v = (double)x[i * inc];
@@ -99,7 +100,7 @@ template <typename T, int MODE> static double reduce_sync(const T* x, size_t cou
     int g = grid_for(count, 8);
     double* partials = reinterpret_cast<double*>(scratch((size_t)g * sizeof(double)));
     const uint64_t seq = box_next();
-    reduce_kernel<T, MODE><<<g, kThreads, 0, c.stream>>>(x, count, inc, partials, c.tickets, nullptr, c.hostbox_dev, seq);
+    launch_pdl(reduce_kernel<T, MODE>, dim3(g), dim3(kThreads), 0, c.stream, x, count, inc, partials, c.tickets, (double*)nullptr, c.hostbox_dev, (unsigned long long)seq);
     TB_LAUNCH_CHECK();
     const double r = box_wait(seq);
     dist_check_fault();
@@ -141,7 +142,7 @@ template <typename T> void l1_sumsq_async(const T* x, size_t n, double* out_dev)
     if (n == 0) { TB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), c.stream)); return; }
     int g = grid_for(n, 8);
     double* partials = reinterpret_cast<double*>(scratch((size_t)g * sizeof(double)));
-    reduce_kernel<T, 0><<<g, kThreads, 0, c.stream>>>(x, n, 1, partials, c.tickets, out_dev, nullptr, 0ull);
+    launch_pdl(reduce_kernel<T, 0>, dim3(g), dim3(kThreads), 0, c.stream, x, n, (size_t)1, partials, c.tickets, out_dev, (double*)nullptr, 0ull);
     TB_LAUNCH_CHECK();
 }
 template void l1_sumsq_async<float>(const float*, size_t, double*);

@@ -19,6 +19,7 @@
 //   * tb_set_scalar_prefetch(0) turns it off; tb_scalar_prefetch_stats reports kernels launched / requests served / dropped.
 #include "common.cuh"
 #include <chrono>
+#include <cstdlib>
 
 namespace tb {
 
@@ -63,6 +64,17 @@ struct PfState {
 };
 PfState g_pf;
 
+// TB_PF_DEBUG=1: one stderr line per request / launch / drop (diagnostics)
+bool pf_debug() {
+    static const bool on = [] { const char* e = std::getenv("TB_PF_DEBUG"); return e && e[0] == '1'; }();
+    return on;
+}
+void pf_log(const char* what, const PfReq& r, const char* extra = "") {
+    if (!pf_debug()) return;
+    std::fprintf(stderr, "[pf] %-8s kind=%d dt=%d a=(%lld,%zu,%zu) b=(%lld,%zu,%zu) y=(%lld,%zu,%zu) %s\n", what, r.kind, r.dtype, (long long)r.a.buf, r.a.off, r.a.len,
+                 (long long)r.b.buf, r.b.off, r.b.len, (long long)r.y.buf, r.y.off, r.y.len, extra);
+}
+
 struct PfJob { const void* a; const void* b; unsigned long long n; int kind; int f64; };
 struct PfJobs {
     int n_jobs;
@@ -91,6 +103,7 @@ template <typename T> __device__ __forceinline__ double pf_partial(const PfJob& 
 __global__ void __launch_bounds__(256) prefetch_reduce_kernel(const __grid_constant__ PfJobs J) {
     __shared__ double red[32];
     __shared__ bool last;
+    tbd::pdl_entry();
     for (int k = 0; k < J.n_jobs; ++k) {
         const double acc = J.job[k].f64 ? pf_partial<double>(J.job[k]) : pf_partial<float>(J.job[k]);
         const double s = tbd::block_sum(acc, red);
@@ -133,6 +146,7 @@ void commit(PfChain&& ch) {
 // one host-visible request (served from the box, or about to miss): learn the chains, and on a miss arm the followers
 void on_request(const PfReq& r, bool was_served) {
     PfState& S = g_pf;
+    pf_log(was_served ? "served" : "miss", r);
     if (r.kind != 0)
         for (PfChain& ch : S.open)
             if (ch.followers.size() < (size_t)kMaxJobs) ch.followers.push_back(r);
@@ -199,10 +213,12 @@ void pf_before_wait() {
             }
             j.n = f.a.len;
             if (j.n == 0) continue;
+            pf_log("launch", f);
             live.push_back(PfLive{f, J.n_jobs, true});
             J.job[J.n_jobs++] = j;
             max_n = std::max<size_t>(max_n, j.n);
         } catch (const Error&) {
+            pf_log("skip", f);
             continue;                     // a view learnt from an earlier buffer generation no longer resolves: skip it
         }
     }
@@ -217,7 +233,7 @@ void pf_before_wait() {
     J.ticket = c.tickets + 40;
     J.box = c.hostbox_dev;
     J.seq = ++S.seq_counter;
-    prefetch_reduce_kernel<<<g, 256, 0, c.stream.raw>>>(J);
+    launch_pdl(prefetch_reduce_kernel, dim3(g), dim3(256), 0, c.stream.raw, J);
     TB_LAUNCH_CHECK();
     S.live = std::move(live);
     S.live_trigger = S.armed_trigger;
@@ -231,6 +247,7 @@ void pf_note_write(tb_handle buf, size_t off, size_t len) {
         if (!e.valid) continue;
         if (overlaps(e.req.a, buf, off, len) || (e.req.kind == 2 && overlaps(e.req.b, buf, off, len))) {
             e.valid = false;
+            pf_log("drop", e.req);
             if (S.bad.size() >= 64) S.bad.erase(S.bad.begin());
             S.bad.push_back({S.live_trigger, e.req});
             S.dropped += 1;
@@ -241,7 +258,7 @@ void pf_note_write(tb_handle buf, size_t off, size_t len) {
 void pf_note_release(tb_handle buf) {
     PfState& S = g_pf;
     for (PfLive& e : S.live)
-        if (e.req.a.buf == buf || e.req.b.buf == buf || e.req.y.buf == buf) e.valid = false;
+        if (e.valid && (e.req.a.buf == buf || e.req.b.buf == buf || e.req.y.buf == buf)) { e.valid = false; pf_log("released", e.req); }
     if (S.have_dot && (S.dot.a.buf == buf || S.dot.b.buf == buf || S.dot.y.buf == buf)) S.have_dot = false;
 }
 

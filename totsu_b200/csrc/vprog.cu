@@ -171,6 +171,7 @@ __device__ __forceinline__ double combine_slot(const double* slot, int g) {
 template <bool CLUSTER>
 __device__ __forceinline__ void run_program(const Program& prog) {
     __shared__ double red[32];
+    tbd::pdl_entry();
     const unsigned rank = CLUSTER ? cluster_ctarank() : blockIdx.x;
     const int g = CLUSTER ? VP_CLUSTER : (int)gridDim.x;
     const size_t gtid = (size_t)rank * VP_THREADS + threadIdx.x;
@@ -310,14 +311,19 @@ void vp_flush() {
     Context& c = ctx();
     R.prog.slots = R.slots;
     R.prog.box = c.hostbox_dev;
-    if (R.wide) {
-        const int g = (int)std::max<size_t>(1, std::min<size_t>((R.max_n + VP_THREADS - 1) / VP_THREADS, (size_t)c.sm_count * 2));
-        vprog_wide_kernel<<<g, VP_THREADS, 0, c.stream.raw>>>(R.prog);
-        c.vprog_wide_launches += 1;
-    } else {
-        vprog_kernel<<<VP_CLUSTER, VP_THREADS, 0, c.stream.raw>>>(R.prog);
+    cudaError_t e = cudaSuccess;
+    try {
+        if (R.wide) {
+            const int g = (int)std::max<size_t>(1, std::min<size_t>((R.max_n + VP_THREADS - 1) / VP_THREADS, (size_t)c.sm_count * 2));
+            launch_pdl(vprog_wide_kernel, dim3(g), dim3(VP_THREADS), 0, c.stream.raw, R.prog);
+            c.vprog_wide_launches += 1;
+        } else {
+            launch_pdl(vprog_kernel, dim3(VP_CLUSTER), dim3(VP_THREADS), 0, c.stream.raw, R.prog);
+        }
+    } catch (const Error&) {
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaErrorLaunchFailure;
     }
-    const cudaError_t e = cudaGetLastError();
     R.prog.n_ops = 0;
     R.next_slot = 0;
     R.wide = false; R.has_barrier = false; R.has_reduction = false; R.max_n = 0;

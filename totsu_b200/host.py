@@ -63,6 +63,8 @@ def hlib():
         L.tbh_set_shim_protocol.argtypes = [i]
         L.tbh_set_shim_protocol.restype = None
         L.tbh_get_shim_protocol.restype = i
+        L.tbh_set_map_eig_fast_paths.argtypes = [i]
+        L.tbh_set_map_eig_fast_paths.restype = None
         _hlib = L
     return _hlib
 
@@ -70,6 +72,11 @@ def hlib():
 def set_shim_protocol(on):
     """Drive the backend with the Rust binding's call protocol (see totsu_b200/host/linalg.hpp); set before creating sessions."""
     hlib().tbh_set_shim_protocol(1 if on else 0)
+
+
+def set_map_eig_fast_paths(on):
+    """B200::map_eig recognises the reference's two closures (ConePSD::proj, MatBuild::set_sqrt) and takes the GEMM-only paths."""
+    hlib().tbh_set_map_eig_fast_paths(1 if on else 0)
 
 
 def _p(a):

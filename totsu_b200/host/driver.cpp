@@ -278,6 +278,9 @@ const char* tbh_last_error(void) { return g_err.c_str(); }
 // host/linalg.hpp "shim-protocol mode"); 0: carry (handle, offset, length) views.  Set before sessions are created.
 void tbh_set_shim_protocol(int on) { shim_protocol() = on != 0; }
 int tbh_get_shim_protocol(void) { return shim_protocol() ? 1 : 0; }
+// 0: B200::map_eig always takes the general closure route (device eigendecomposition + host closure); 1 (default): the two
+// closures the reference itself uses are recognised and served by tb_proj_psd / tb_sqrt_psd
+void tbh_set_map_eig_fast_paths(int on) { map_eig_fast_paths() = on != 0; }
 
 void* tbh_session_lp(int dtype, size_t n, size_t m, size_t p, const void* c, const void* g, const void* h, const void* a, const void* b) {
     return guarded_new([&] { return (void*)DISPATCH(dtype, make_lp, n, m, p, c, g, h, a, b); });

@@ -7,6 +7,7 @@
 // Every method forwards to one C-ABI entry point of libtotsu_b200.so and asserts on its status - the traits
 // have no error channel, exactly like totsu_f32cuda asserts on cuBLAS statuses (f32cuda.rs:38).
 #pragma once
+#include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -51,6 +52,7 @@ template <typename F> struct Abi;
             return tb_map_eig_finish_##S_(m, hs, sd, w, ne, k);                                                            \
         }                                                                                                                  \
         static int proj_psd(tb_view x, F_ ez, tb_view w) { return tb_proj_psd_##S_(x, ez, w); }                            \
+        static int sqrt_psd(tb_view m, F_ ez, tb_view w) { return tb_sqrt_psd_##S_(m, ez, w); }                            \
         static int denseop_apply(tb_handle h, int t, F_ a, tb_view x, F_ b, tb_view y) { return tb_denseop_apply_##S_(h, t, a, x, b, y); } \
         static int denseop_apply_pair(tb_handle h, F_ an, tb_view xn, F_ bn, tb_view yn, F_ at, tb_view xt, F_ bt, tb_view yt) { \
             return tb_denseop_apply_pair_##S_(h, an, xn, bn, yn, at, xt, bt, yt);                                          \
@@ -75,6 +77,11 @@ TBH_ABI(double, f64)
 // ---------------------------------------------------------------------------------------------------------
 inline bool& shim_protocol() {
     static bool on = false;
+    return on;
+}
+// map_eig: recognise the reference's own two closures and take the GEMM-only paths (default on; off = always the general route)
+inline bool& map_eig_fast_paths() {
+    static bool on = true;
     return on;
 }
 
@@ -249,11 +256,41 @@ template <typename F> struct B200 {
 
     // linalg_ex.rs:64.  `map(e, out)` returns false for None, or true with the replacement eigenvalue in `out`.
     // Like dsyevr(range=V, vl=0, vu=+inf) in the CPU twin (f64lapack.rs:86-91) only eigenvalues > 0 reach the closure.
+    // The two closures the reference itself passes to map_eig are recognised by probing them on a fixed set of positive
+    // arguments spanning the floating-point range (only eigenvalues > 0 ever reach the closure, f64lapack.rs:86-107):
+    //   e -> Some(e)        ConePSD::proj (cone_psd.rs:69-76), with scale_diag = Some(sqrt 2)  -> tb_proj_psd (GEMM-only sign iteration)
+    //   e -> Some(sqrt(e))  MatBuild::set_sqrt (matbuild/mod.rs:231-238), scale_diag = None    -> tb_sqrt_psd (GEMM-only Newton-Schulz)
+    // so that the UNMODIFIED ConePSD / ProbQP / ProbQCQP get the fast paths through the trait surface; any other closure
+    // takes the general route below (eigendecomposition on the device, eigenvalues through the closure on the host).
+    enum class Closure { General, KeepPositive, Sqrt };
+    static Closure recognise(const std::function<bool(F, F&)>& map) {
+        static const double probes[] = {1e-30, 3e-21, 1e-12, 7e-7, 1e-3, 0.25, 1.0, 2.0, 9.0, 1234.5, 1e6, 3e12, 1e20, 1e30};
+        bool keep = true, root = true;
+        for (double pd : probes) {
+            const F e = (F)pd;
+            F out = F(0);
+            if (!map(e, out)) return Closure::General;
+            keep = keep && out == e;
+            root = root && out == (F)std::sqrt(e);
+        }
+        return keep ? Closure::KeepPositive : root ? Closure::Sqrt : Closure::General;
+    }
     static void map_eig(Sl& mat, bool has_scale, F scale_diag, F eps_zero, Sl& work, const std::function<bool(F, F&)>& map) {
         const size_t sn = mat.len();
         size_t n = 0;
         while ((n + 1) * (n + 2) / 2 <= sn) ++n;
         if (n * (n + 1) / 2 != sn) throw BackendError("map_eig: length is not a triangular number");
+        if (map_eig_fast_paths()) {
+            const Closure cl = recognise(map);
+            if (cl == Closure::KeepPositive && has_scale && scale_diag == (F)std::sqrt(F(2))) {
+                TBH_CALL(Abi<F>::proj_psd(mat.view(), eps_zero, work.view()));
+                return;
+            }
+            if (cl == Closure::Sqrt && !has_scale) {
+                TBH_CALL(Abi<F>::sqrt_psd(mat.view(), eps_zero, work.view()));
+                return;
+            }
+        }
         std::vector<F> eigs(n), neweigs(n);
         std::vector<uint8_t> keep(n);
         TBH_CALL(Abi<F>::map_eig_begin(mat.view(), has_scale ? 1 : 0, scale_diag, eps_zero, work.view(), eigs.data()));
