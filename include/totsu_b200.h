@@ -154,6 +154,8 @@ int tb_transform_ge_f64(int transpose, size_t n_row, size_t n_col, double alpha,
 /* y = alpha*S*x + beta*y; S symmetric, upper triangle packed by columns (linalg_ex.rs:37) */
 int tb_transform_sp_f32(size_t n, float alpha, tb_view mat, tb_view x, float beta, tb_view y);
 int tb_transform_sp_f64(size_t n, double alpha, tb_view mat, tb_view x, double beta, tb_view y);
+/* consumer warps of the streaming transform_sp kernel: 8 (default) or 16 (two warps per column in the column pass; measured slower) */
+int tb_set_spmv_warps(int warps);
 /* linalg_ex.rs:43 */
 size_t tb_map_eig_worklen(size_t n);
 /* linalg_ex.rs:64 map_eig, split around the host closure `map: Fn(F)->Option<F>`:

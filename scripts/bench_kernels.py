@@ -74,8 +74,11 @@ def main():
     x, y = capi.Buf(dtype=dt, length=n), capi.Buf(dtype=dt, length=n)
     x.upload(rng.standard_normal(n).astype(dt))
     spf = capi.fn("tb_transform_sp", dt)
-    row("transform_sp (spmv_kernel + finalize), n = 8192 packed", timed(lambda: capi.check(spf(n, 1.0, sp.view(), x.view(), 0.0, y.view())), 10, True), n * (n + 1) // 2 * 4,
-        "134 MB: L2 flushed between repetitions")
+    for warps in (8, 16):
+        capi.check(L.tb_set_spmv_warps(warps))
+        row("transform_sp (spmv_stream_kernel, %d consumer warps + finalize), n = 8192 packed" % warps,
+            timed(lambda: capi.check(spf(n, 1.0, sp.view(), x.view(), 0.0, y.view())), 10, True), n * (n + 1) // 2 * 4, "134 MB: L2 flushed between repetitions")
+    capi.check(L.tb_set_spmv_warps(8))
     for bf in (sp, x, y):
         bf.release()
 

@@ -207,9 +207,9 @@ def test_sqrt_psd_vs_oracle(dt, k, kind):
     if kind == "indefinite":
         assert route.value == 2
     scale = np.abs(want_m).max()
-    # sqrt is ill-conditioned at 0: compare S (to sqrt of the working precision for rank-deficient P) and S^2 = P+ (tight)
-    tol_s = {"full": 3e-5, "diag": 3e-5, "lowrank": 3e-3, "indefinite": 3e-3}[kind] if dt == np.float32 else \
-            {"full": 1e-11, "diag": 1e-11, "lowrank": 1e-6, "indefinite": 1e-8}[kind]
+    # f32 rounding of the GEMM chain grows with k (4e-5 at 2048); sqrt is ill-conditioned at 0: compare S (to sqrt of the working precision for rank-deficient P) and S^2 = P+ (tight)
+    tol_s = {"full": 3e-5 * max(1, k // 512), "diag": 3e-5, "lowrank": 3e-3, "indefinite": 3e-3}[kind] if dt == np.float32 else \
+            {"full": 1e-11, "diag": 1e-11, "lowrank": 1e-5, "indefinite": 1e-8}[kind]        # lowrank: eigenvalues below eps_zero = 1e-12 are dropped, sqrt(1e-12) = 1e-6 each
     assert np.abs(got - want_m).max() <= tol_s * scale, (np.abs(got - want_m).max() / scale, route.value, iters.value)
     p_plus = (v * np.maximum(w, 0.0)) @ v.T
     tol_p = 1e-4 if dt == np.float32 else 1e-10

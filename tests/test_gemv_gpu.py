@@ -91,9 +91,22 @@ def test_transform_ge_auto_path_and_errors(dt):
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("n", [1, 2, 5, 16, 17, 100, 511, 512, 513, 1024, 1025, 2050, 4099, 6000])
-def test_transform_sp(dt, n):
+@pytest.mark.parametrize("warps", [8, 16])
+def test_transform_sp(dt, n, warps):
     """n < 512 (and unaligned views): generic kernel; n >= 512: the TMA streaming kernel (sizes chosen so that the
-    packed length leaves 0..3 trailing elements outside the last aligned 16-byte window, and chunks are ragged)."""
+    packed length leaves 0..3 trailing elements outside the last aligned 16-byte window, and chunks are ragged), with 8
+    consumer warps (the default) and with 16 (two per column in the column pass).  Work units are dealt to the CTAs by a
+    device-side queue; partials are indexed by unit, so the result does not depend on the dealing."""
+    if n < 512 and warps == 16:
+        pytest.skip("the generic kernel has no warp variants")
+    capi.check(capi.lib().tb_set_spmv_warps(warps))
+    try:
+        _transform_sp_case(dt, n)
+    finally:
+        capi.check(capi.lib().tb_set_spmv_warps(8))
+
+
+def _transform_sp_case(dt, n):
     rng = np.random.default_rng(n)
     sp = rng.standard_normal(n * (n + 1) // 2).astype(dt)
     x = rng.standard_normal(n).astype(dt)

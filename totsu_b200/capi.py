@@ -52,7 +52,7 @@ def _signatures():
     sig = {
         "tb_init": (i, [i]), "tb_shutdown": (i, []), "tb_last_error": (C.c_char_p, []), "tb_device_sync": (i, []),
         "tb_get_stream": (i, [C.POINTER(vp)]), "tb_sm_count": (i, [C.POINTER(i)]),
-        "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_pdl": (i, [i]), "tb_set_psd_path": (i, [i]),
+        "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_pdl": (i, [i]), "tb_set_spmv_warps": (i, [i]), "tb_set_psd_path": (i, [i]),
         "tb_set_pair_fusion": (i, [i]), "tb_pairs_fused": (i, [C.POINTER(u64)]),
         "tb_host_wait_stats": (i, [C.POINTER(C.c_double), C.POINTER(u64)]),
         "tb_set_psd_pairing": (i, [i]), "tb_psd_pairs": (i, [C.POINTER(u64)]),

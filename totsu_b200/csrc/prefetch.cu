@@ -12,8 +12,9 @@
 //   * nothing about the solver is hard-wired: the library learns "request R was followed by requests F1..F4" from the call
 //     stream (a request = plain element fetch | sum of squares of a view | dot product into a 1-element view + its fetch);
 //   * validity: every device write goes through dev_ptr(write) -> spec_note_write -> pf_note_write; a write that overlaps the
-//     inputs of a prefetched reduction drops it and marks (R -> F) as not worth prefetching again (|p| at the time kappa is
-//     read is learnt that way after one wasted attempt);
+//     inputs of a prefetched reduction drops it; if F is then still requested, (R -> F) is marked as not worth prefetching
+//     again (|p| at the time kappa is read is learnt that way after one wasted attempt); if F is simply not requested this
+//     time round (the criteria_inf branch skips |d|), nothing is marked;
 //   * alpha is applied at serve time with the arithmetic of the kernel it replaces; the reduction itself is accumulated in
 //     double like the vector-program reductions (results agree with the un-prefetched path to rounding, not bit for bit);
 //   * tb_set_scalar_prefetch(0) turns it off; tb_scalar_prefetch_stats reports kernels launched / requests served / dropped.
@@ -39,7 +40,7 @@ inline bool overlaps(const tb_view& v, tb_handle buf, size_t off, size_t len) {
     return v.buf == buf && v.len > 0 && len > 0 && v.off < off + len && off < v.off + v.len;
 }
 
-struct PfChain { PfReq trigger; std::vector<PfReq> followers; };
+struct PfChain { PfReq trigger; std::vector<PfReq> followers; std::vector<int> unseen; };      // unseen[i]: rounds in a row follower i was not asked for
 struct PfLive { PfReq req; int slot; bool valid; };
 
 constexpr int kMaxJobs = 4;
@@ -49,7 +50,8 @@ constexpr int kBoxSeq = 8;
 struct PfState {
     bool on = true;
     std::vector<PfChain> table, open;
-    std::vector<std::pair<PfReq, PfReq>> bad;
+    std::vector<std::pair<PfReq, PfReq>> bad;         // (trigger, follower): the follower's inputs change between the two requests - never prefetch
+    std::vector<std::pair<PfReq, PfReq>> suspect;     // a prefetched value was overwritten unread: bad only if the request then still comes
     std::vector<PfLive> live;
     PfReq live_trigger;
     uint64_t live_seq = 0;
@@ -135,10 +137,27 @@ bool is_bad(const PfReq& trig, const PfReq& f) {
     return false;
 }
 
+// A finished chain replaces what was known about its trigger - except that followers seen in earlier rounds and not in this one
+// are kept for a few rounds: a solver iteration that takes the other branch (criteria_inf asks for |d| only when b.y > eps_zero)
+// must not make the next ordinary iteration pay a round trip to re-learn |p| -> |d|.
 void commit(PfChain&& ch) {
     PfState& S = g_pf;
-    for (PfChain& t : S.table)
-        if (req_eq(t.trigger, ch.trigger)) { t.followers = std::move(ch.followers); return; }
+    ch.unseen.assign(ch.followers.size(), 0);
+    for (PfChain& t : S.table) {
+        if (!req_eq(t.trigger, ch.trigger)) continue;
+        for (size_t i = 0; i < t.followers.size(); ++i) {
+            bool seen = false;
+            for (const PfReq& f : ch.followers) seen = seen || req_eq(f, t.followers[i]);
+            const int unseen = i < t.unseen.size() ? t.unseen[i] + 1 : 1;
+            if (!seen && unseen < 8 && ch.followers.size() < (size_t)kMaxJobs) {
+                ch.followers.push_back(t.followers[i]);
+                ch.unseen.push_back(unseen);
+            }
+        }
+        t.followers = std::move(ch.followers);
+        t.unseen = std::move(ch.unseen);
+        return;
+    }
     if (S.table.size() >= 32) S.table.erase(S.table.begin());
     S.table.push_back(std::move(ch));
 }
@@ -147,6 +166,23 @@ void commit(PfChain&& ch) {
 void on_request(const PfReq& r, bool was_served) {
     PfState& S = g_pf;
     pf_log(was_served ? "served" : "miss", r);
+    // A prefetched value of r was overwritten before r was asked for, and now r IS asked for (from the device, or from a later
+    // trigger's prefetch): its inputs change between that trigger and the request (|p| and |d| at the time kappa is read) -
+    // structural, never prefetch it on that trigger again.  A suspect whose trigger comes round again without the request
+    // having been made was only a branch not taken this time (criteria_inf asks for |d| only when b.y > eps_zero,
+    // solver.rs:650-655) and stays prefetchable.
+    for (size_t i = 0; i < S.suspect.size();) {
+        if (req_eq(S.suspect[i].second, r)) {
+            if (S.bad.size() >= 64) S.bad.erase(S.bad.begin());
+            S.bad.push_back(S.suspect[i]);
+            pf_log("bad", r);
+            S.suspect.erase(S.suspect.begin() + (long)i);
+        } else if (!was_served && req_eq(S.suspect[i].first, r)) {
+            S.suspect.erase(S.suspect.begin() + (long)i);
+        } else {
+            ++i;
+        }
+    }
     if (r.kind != 0)
         for (PfChain& ch : S.open)
             if (ch.followers.size() < (size_t)kMaxJobs) ch.followers.push_back(r);
@@ -155,7 +191,7 @@ void on_request(const PfReq& r, bool was_served) {
         S.open.clear();
     }
     if (!was_served) {
-        if (S.open.size() < 8) S.open.push_back(PfChain{r, {}});
+        if (S.open.size() < 8) S.open.push_back(PfChain{r, {}, {}});
         S.armed.clear();
         for (const PfChain& t : S.table) {
             if (!req_eq(t.trigger, r)) continue;
@@ -248,8 +284,8 @@ void pf_note_write(tb_handle buf, size_t off, size_t len) {
         if (overlaps(e.req.a, buf, off, len) || (e.req.kind == 2 && overlaps(e.req.b, buf, off, len))) {
             e.valid = false;
             pf_log("drop", e.req);
-            if (S.bad.size() >= 64) S.bad.erase(S.bad.begin());
-            S.bad.push_back({S.live_trigger, e.req});
+            if (S.suspect.size() >= 64) S.suspect.erase(S.suspect.begin());
+            S.suspect.push_back({S.live_trigger, e.req});
             S.dropped += 1;
         }
     }
@@ -264,7 +300,7 @@ void pf_note_release(tb_handle buf) {
 
 void pf_reset() {
     PfState& S = g_pf;
-    S.table.clear(); S.open.clear(); S.bad.clear(); S.live.clear(); S.armed.clear();
+    S.table.clear(); S.open.clear(); S.bad.clear(); S.suspect.clear(); S.live.clear(); S.armed.clear();
     S.have_dot = false;
 }
 

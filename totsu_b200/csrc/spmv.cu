@@ -111,14 +111,21 @@ __global__ void spmv_finalize(const T* __restrict__ part_r, const T* __restrict_
 // The last total % VEC elements of the array cannot be fetched by an aligned window without reading past the end; the
 // finalize kernel adds their (<= 3) contributions directly.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int SPS_WARPS = 8;
+constexpr int SPS_WARPS = 8;             // consumer warps of the base variant; the chunk height TR = 256 * VEC is fixed by it
 constexpr int SPS_CONSUMERS = SPS_WARPS * 32;
 constexpr int SPS_THREADS = SPS_CONSUMERS + 32;
 constexpr int SPS_TC = 8;               // columns per tile
+// H = 1 (default): 8 consumer warps (one per column in the column pass, 4 rows per thread in the row pass).  H = 2: 16 consumer
+// warps - two warps share a column (upper / lower half of the chunk's rows) and a thread owns 2 rows: the same shared-memory
+// reads spread over twice the warps.  Built to test the round-1 reading of the ncu capture ("consumers latency-bound, 2 warps per
+// scheduler"); measured on B200 it is 7-19 % SLOWER (profiles/r02_spmv_summary.md): the consumers were never the limit, the
+// static split of the triangle over the CTAs was (SMs idle 36 % of the kernel) - hence the unit queue below.
+// tb_set_spmv_warps selects; the finalize kernel sums H column-pass partials per (chunk, column).
 constexpr int SPS_MAX_UNIT_COLS = 2048;
 constexpr size_t SPS_XRES_BYTES = 49152;     // x resident in shared memory up to this size
 
 struct SpUnit { int chunk, split, tile0, tile1; };
+static int g_spmv_halves = 1;            // consumer warps / 8 of the streaming kernel (tb_set_spmv_warps); 8 warps measured faster (below)
 
 // Shift of column c's segment inside its 16-byte-aligned window: (c(c+1)/2 + row0) mod VEC.  row0 is a multiple of VEC and
 // a tile starts at a multiple of 8, so the shift depends only on the column's slot j = c mod 8 in the tile:
@@ -132,51 +139,75 @@ struct SpParams {
     const void* x;
     void* part_n;            // [max_splits][n]
     void* part_t;            // [n_chunks][n]
-    const SpUnit* units;
-    const int* cta_begin;    // [gridDim.x + 1]
+    const SpUnit* units;     // heaviest first
+    int n_units;
+    int* next_unit;          // work-queue head: CTAs take units in order with atomicAdd; the finalize kernel resets it to 0
     int tail;                // trailing elements of the array left to the finalize kernel
 };
 
 // XRES: all of x lives in shared memory for the whole kernel (n * sizeof(T) <= 48 KB, one ring stage fewer); otherwise each
 // work unit stages the x slice of its columns and re-reads the x of its rows from L2.
-template <typename T, bool XRES>
-__global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpParams p) {
+template <typename T, bool XRES, int H>
+__global__ void __launch_bounds__(SPS_CONSUMERS * H + 32, 1) spmv_stream_kernel(const SpParams p) {
     constexpr int SPS_STAGES = XRES ? 5 : 6;
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int TR = SPS_CONSUMERS * VEC;          // rows per chunk: 1024 (f32) / 512 (f64)
     constexpr int SLOT = TR + VEC;                   // staged elements per column: the aligned window may start VEC-1 early
     constexpr int STAGE_ELEMS = SPS_TC * SLOT;
-    constexpr int KT = TR / 32;                      // rows per lane in the column pass
+    constexpr int CONS = SPS_CONSUMERS * H;          // consumer threads
+    constexpr int NW = SPS_WARPS * H;                // consumer warps; warp NW is the producer
+    constexpr int RPT = TR / CONS;                   // rows per thread in the row pass: thread t owns rows t + CONS * i
+    constexpr int HR = TR / H;                       // rows per warp in the column pass: warp w takes rows [(w / 8) * HR, +HR) of column w % 8
+    constexpr int KT = HR / 32;                      // rows per lane in the column pass
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* stage_base = reinterpret_cast<T*>(smem_raw);
     T* xs = stage_base + (size_t)SPS_STAGES * STAGE_ELEMS;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(xs + (XRES ? SPS_XRES_BYTES / sizeof(T) : (size_t)SPS_MAX_UNIT_COLS));
     uint64_t* empty_bar = full_bar + SPS_STAGES;
+    int4* stage_unit = reinterpret_cast<int4*>(empty_bar + SPS_STAGES);      // descriptor of the unit the tile in each stage belongs to (16-byte aligned); chunk < 0: no more work
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const T* __restrict__ S = reinterpret_cast<const T*>(p.S);
     const size_t n = p.n;
     if (tid == 0) {
-        for (int s = 0; s < SPS_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], SPS_WARPS); }
+        for (int s = 0; s < SPS_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], NW); }
         ptx::mbar_fence_init();
     }
+    tbd::pdl_entry();          // barrier set-up overlaps the tail of the previous kernel; no global access before this point
     __syncthreads();
-    const int u_begin = p.cta_begin[blockIdx.x], u_end = p.cta_begin[blockIdx.x + 1];
     const size_t last_lim = n - (size_t)p.tail;      // exclusive row limit of the last column
-    if (XRES && warp < SPS_WARPS) {
+    if (XRES && warp < NW) {
         const T* __restrict__ xg = reinterpret_cast<const T*>(p.x);
-        for (size_t i = tid; i < n; i += SPS_CONSUMERS) xs[i] = xg[i];
-        ptx::named_bar_sync(1, SPS_CONSUMERS);
+        for (size_t i = tid; i < n; i += CONS) xs[i] = xg[i];
+        ptx::named_bar_sync(1, CONS);
     }
+    const int cw = warp % SPS_WARPS, ch = warp / SPS_WARPS;      // column-pass role: column slot and row half of this warp
+    const int hb = ch * HR;                                      // first chunk-local row of this warp's half
 
-    if (warp == SPS_WARPS) {
+    if (warp == NW) {
         // ===================== producer warp =====================
         const uint64_t pol = ptx::policy_evict_first();
         int s = 0;
         uint32_t phase = 0;
-        for (int u = u_begin; u < u_end; ++u) {
-            const SpUnit un = p.units[u];
+        // Units are taken from a global queue (atomicAdd), heaviest first: the triangle makes units unequal (tiles cut by the
+        // diagonal cost ~3x a dense tile) and a static split left SMs idle 36 % of the kernel (ncu r02: sm__cycles_active avg
+        // 143 k vs max 216 k at n = 16384).  The unit id travels to the consumers with the tile (stage_unit, published by the
+        // arrive on full_bar); results do not depend on which CTA ran a unit: partials are indexed by (chunk, split) only.
+        // The queue is read one unit ahead (the atomic for unit i+1 is in flight while unit i streams; reading further ahead would
+        // let a CTA sit on units that idle CTAs could take at the end of the kernel).  The descriptor load at the start of a unit is
+        // an L2 round trip on the producer only: the ring holds several tiles of slack.
+        int pend = 0;                                     // lane 0: result of the atomic in flight
+        if (lane == 0) pend = atomicAdd(p.next_unit, 1);
+        for (;;) {
+            const int u_cur = __shfl_sync(0xffffffffu, pend, 0);
+            if (u_cur >= p.n_units) {
+                ptx::mbar_wait(&empty_bar[s], phase ^ 1);
+                if (lane == 0) { stage_unit[s] = make_int4(-1, 0, 0, 0); ptx::mbar_arrive(&full_bar[s]); }
+                break;
+            }
+            const SpUnit un = p.units[u_cur];
+            if (lane == 0) pend = atomicAdd(p.next_unit, 1);
             const size_t row0 = (size_t)un.chunk * TR;
             for (int t = un.tile0; t < un.tile1; ++t) {
                 const size_t c = (size_t)t * SPS_TC + lane;
@@ -194,7 +225,7 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
                 }
                 const uint32_t tile_bytes = __reduce_add_sync(0xffffffffu, bytes);
                 ptx::mbar_wait(&empty_bar[s], phase ^ 1);
-                if (lane == 0) ptx::mbar_expect_tx(&full_bar[s], tile_bytes);
+                if (lane == 0) { stage_unit[s] = make_int4(un.chunk, un.split, un.tile0, un.tile1); ptx::mbar_expect_tx(&full_bar[s], tile_bytes); }
                 __syncwarp();
                 if (bytes) ptx::bulk_g2s(stage_base + (size_t)s * STAGE_ELEMS + (size_t)lane * SLOT, src, bytes, &full_bar[s], pol);
                 if (++s == SPS_STAGES) { s = 0; phase ^= 1; }
@@ -207,30 +238,34 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
         T* __restrict__ part_t = reinterpret_cast<T*>(p.part_t);
         int s = 0;
         uint32_t phase = 0;
-        for (int u = u_begin; u < u_end; ++u) {
-            const SpUnit un = p.units[u];
+        for (;;) {
+            // the first tile of the next unit (or the end mark) is already on its way: its stage names the unit
+            ptx::mbar_wait(&full_bar[s], phase);
+            const int4 ud = stage_unit[s];
+            if (ud.x < 0) break;
+            const SpUnit un{ud.x, ud.y, ud.z, ud.w};
             const size_t row0 = (size_t)un.chunk * TR;
             const size_t c0 = (size_t)un.tile0 * SPS_TC;
             const size_t c1 = (size_t)un.tile1 * SPS_TC < n ? (size_t)un.tile1 * SPS_TC : n;
             const int ucols = (int)(c1 - c0);
             if (!XRES) {
                 // stage x[c] of this unit's columns (the previous unit's readers are done: barrier first)
-                ptx::named_bar_sync(1, SPS_CONSUMERS);
-                for (int i = tid; i < ucols; i += SPS_CONSUMERS) xs[i] = x[c0 + i];
-                ptx::named_bar_sync(1, SPS_CONSUMERS);
+                ptx::named_bar_sync(1, CONS);
+                for (int i = tid; i < ucols; i += CONS) xs[i] = x[c0 + i];
+                ptx::named_bar_sync(1, CONS);
             }
             const T* xcol = XRES ? xs + c0 : xs;      // x of the unit's columns, indexed from the unit's first column
-            // column pass: x of the rows this lane strides over (rows lane + 32 k of the chunk)
+            // column pass: x of the rows this lane strides over (rows hb + lane + 32 k of the chunk)
             T xr[KT];
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
-                const size_t r = row0 + lane + 32 * k;
+                const size_t r = row0 + hb + lane + 32 * k;
                 xr[k] = r < n ? (XRES ? xs[r] : x[r]) : T(0);
             }
-            // row pass: thread t owns rows t + 256 i of the chunk (conflict-free scalar LDS)
-            T acc[VEC];
+            // row pass: thread t owns rows t + CONS * i of the chunk (conflict-free scalar LDS)
+            T acc[RPT];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = T(0);
+            for (int i = 0; i < RPT; ++i) acc[i] = T(0);
 
             int cl = 0;
             for (int t = un.tile0; t < un.tile1; ++t, cl += SPS_TC) {
@@ -246,9 +281,9 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
                         const T* col = tile + (size_t)j * SLOT + sp_shift<VEC>(j);
                         const T xv = xcol[cl + j];
 #pragma unroll
-                        for (int i = 0; i < VEC; ++i) acc[i] += col[tid + SPS_CONSUMERS * i] * xv;
+                        for (int i = 0; i < RPT; ++i) acc[i] += col[tid + CONS * i] * xv;
                     }
-                    const T* col = tile + (size_t)warp * SLOT + sp_shift<VEC>(warp);
+                    const T* col = tile + (size_t)cw * SLOT + sp_shift<VEC>(cw) + hb;
                     T sum0 = T(0), sum1 = T(0), sum2 = T(0), sum3 = T(0);
 #pragma unroll
                     for (int k = 0; k < KT; k += 4) {
@@ -258,7 +293,7 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
                         sum3 += col[lane + 32 * (k + 3)] * xr[k + 3];
                     }
                     const T sum = tbd::warp_sum((sum0 + sum1) + (sum2 + sum3));
-                    if (lane == 0) part_t[(size_t)un.chunk * n + ct + warp] = sum;
+                    if (lane == 0) part_t[((size_t)un.chunk * H + ch) * n + ct + cw] = sum;
                 } else {
                     // per-column limits in chunk-local rows: rows < lim_t are staged (column pass), rows < lim_n also skip the
                     // diagonal (row pass); right of the chunk's diagonal block both are >= TR and mask nothing
@@ -273,19 +308,19 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
                             const T* col = tile + (size_t)j * SLOT + sp_shift<VEC>(j);
                             const T xv = xcol[cl + j];
     #pragma unroll
-                            for (int i = 0; i < VEC; ++i)
-                                if (warp * 32 + SPS_CONSUMERS * i < lim_n) {       // warp-uniform skip of rows below the diagonal
-                                    if (tid + SPS_CONSUMERS * i < lim_n) acc[i] += col[tid + SPS_CONSUMERS * i] * xv;
+                            for (int i = 0; i < RPT; ++i)
+                                if (warp * 32 + CONS * i < lim_n) {       // warp-uniform skip of rows below the diagonal
+                                    if (tid + CONS * i < lim_n) acc[i] += col[tid + CONS * i] * xv;
                                 }
                         }
                     }
-                    if (warp < ncols) {
-                        const size_t c = ct + warp;
-                        long long lim_t = d0 + warp + 1;
+                    if (cw < ncols) {
+                        const size_t c = ct + cw;
+                        long long lim_t = d0 + cw + 1;
                         if (c == n - 1) lim_t = (long long)last_lim - (long long)row0;
-                        const T* col = tile + (size_t)warp * SLOT + sp_shift<VEC>(warp);
+                        const T* col = tile + (size_t)cw * SLOT + sp_shift<VEC>(cw) + hb;
                         T sum0 = T(0), sum1 = T(0), sum2 = T(0), sum3 = T(0);
-                        const int lim = lim_t > (long long)TR ? TR : (int)lim_t;
+                        const int lim = (lim_t > (long long)TR ? TR : (int)lim_t) - hb;      // rows of this warp's half that are staged
     #pragma unroll
                         for (int k = 0; k < KT; k += 4) {
                             if (32 * k >= lim) break;                 // warp-uniform: nothing staged below the diagonal
@@ -295,7 +330,7 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
                             if (lane + 32 * (k + 3) < lim) sum3 += col[lane + 32 * (k + 3)] * xr[k + 3];
                         }
                         const T sum = tbd::warp_sum((sum0 + sum1) + (sum2 + sum3));
-                        if (lane == 0) part_t[(size_t)un.chunk * n + c] = sum;
+                        if (lane == 0) part_t[((size_t)un.chunk * H + ch) * n + c] = sum;
                     }
                 }
                 __syncwarp();
@@ -303,8 +338,8 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
                 if (++s == SPS_STAGES) { s = 0; phase ^= 1; }
             }
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const size_t r = row0 + tid + SPS_CONSUMERS * i;
+            for (int i = 0; i < RPT; ++i) {
+                const size_t r = row0 + tid + CONS * i;
                 if (r < n) part_n[(size_t)un.split * n + r] = acc[i];
             }
         }
@@ -316,21 +351,39 @@ __global__ void __launch_bounds__(SPS_THREADS, 1) spmv_stream_kernel(const SpPar
 // sub-sums are added in a fixed order.
 template <typename T>
 __global__ void __launch_bounds__(256) spmv_stream_finalize(const T* __restrict__ part_n, const T* __restrict__ part_t, const T* __restrict__ S,
-                                                            const T* __restrict__ x, size_t n, size_t total, int tail, int tiles_per_unit,
-                                                            T alpha, T beta, T* y) {
+                                                            const T* __restrict__ x, size_t n, size_t total, int tail, const int* __restrict__ chunk_splits,
+                                                            int halves, T alpha, T beta, T* y, int* next_unit) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr size_t TR = (size_t)SPS_CONSUMERS * VEC;
     __shared__ T red[8][33];
+    tbd::pdl_entry();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_unit = 0;          // the streaming kernel's work queue, for its next launch
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t i = blockIdx.x * (size_t)32 + lane;
     T v = T(0);
     if (i < n) {
         const size_t chunk = i / TR;
-        const size_t n_tiles = (n + SPS_TC - 1) / SPS_TC;
-        const size_t tiles_r = n_tiles - chunk * (TR / SPS_TC);
-        const size_t splits = (tiles_r + tiles_per_unit - 1) / tiles_per_unit;
-        for (size_t s = w; s < splits; s += 8) v += part_n[s * n + i];
-        for (size_t r = w; r <= chunk; r += 8) v += part_t[r * n + i];
+        const size_t splits = (size_t)chunk_splits[chunk];
+        // four independent loads in flight per thread (the partials are L2-resident; a serial chain would pay one L2 round trip each)
+        size_t sidx = w;
+        T v0 = T(0), v1 = T(0), v2 = T(0), v3 = T(0);
+        for (; sidx + 24 < splits; sidx += 32) {
+            v0 += part_n[sidx * n + i];
+            v1 += part_n[(sidx + 8) * n + i];
+            v2 += part_n[(sidx + 16) * n + i];
+            v3 += part_n[(sidx + 24) * n + i];
+        }
+        for (; sidx < splits; sidx += 8) v0 += part_n[sidx * n + i];
+        const size_t n_t = (chunk + 1) * (size_t)halves;
+        size_t r = w;
+        for (; r + 24 < n_t; r += 32) {
+            v0 += part_t[r * n + i];
+            v1 += part_t[(r + 8) * n + i];
+            v2 += part_t[(r + 16) * n + i];
+            v3 += part_t[(r + 24) * n + i];
+        }
+        for (; r < n_t; r += 8) v1 += part_t[r * n + i];
+        v = (v0 + v1) + (v2 + v3);
     }
     red[w][lane] = v;
     __syncthreads();
@@ -356,8 +409,9 @@ __global__ void __launch_bounds__(256) spmv_stream_finalize(const T* __restrict_
 
 struct SpPlan {
     SpUnit* units_dev = nullptr;
-    int* cta_begin_dev = nullptr;
-    int grid = 0, max_splits = 0, n_chunks = 0, tiles_per_unit = 0;
+    int* next_unit_dev = nullptr;
+    int* chunk_splits_dev = nullptr;      // [n_chunks]: units (= row-pass partials) per row chunk
+    int grid = 0, n_units = 0, max_splits = 0, n_chunks = 0;
 };
 
 template <typename T> static const SpPlan& spmv_plan(size_t n) {
@@ -367,51 +421,61 @@ template <typename T> static const SpPlan& spmv_plan(size_t n) {
     constexpr size_t VEC = 16 / sizeof(T);
     constexpr size_t TR = (size_t)SPS_CONSUMERS * VEC;
     const size_t n_tiles = (n + SPS_TC - 1) / SPS_TC, n_chunks = (n + TR - 1) / TR;
-    size_t total_tiles = 0;
-    for (size_t R = 0; R < n_chunks; ++R) total_tiles += n_tiles - R * (TR / SPS_TC);
     const size_t n_cta = (size_t)ctx().sm_count;
-    const size_t per_cta = n * sizeof(T) <= SPS_XRES_BYTES ? 4 : 2;      // units are cheap when x is resident in shared memory
-    size_t tpu = (total_tiles + per_cta * n_cta - 1) / (per_cta * n_cta);
-    tpu = std::max<size_t>(1, std::min<size_t>(tpu, SPS_MAX_UNIT_COLS / SPS_TC));
+    // Consumer cost, not bytes, is what a tile takes: a tile cut by the diagonal (or holding the last column) runs the masked path,
+    // measured ~3x the instructions of a dense tile (ncu, profiles/r01_spmv_stream_full.md).
+    auto tile_weight = [&](size_t R, size_t t) {
+        const size_t ct = t * SPS_TC, row0 = R * TR;
+        return (ct >= row0 + TR && ct + SPS_TC < n) ? 1.0 : 3.0;
+    };
+    double w_total = 0.0;
+    for (size_t R = 0; R < n_chunks; ++R)
+        for (size_t t = R * (TR / SPS_TC); t < n_tiles; ++t) w_total += tile_weight(R, t);
+    // Guided unit sizes: the first 3/4 of every chunk's weight is cut into units of 1/4 of a CTA's share (few units: each costs a
+    // row-pass partial and a pipeline hand-over), the last quarter into units of 1/16 of a share, and the queue serves the big
+    // ones first - the tail of the kernel is then at most 1/16 of a share (~6 %) long.
+    const double share = w_total / (double)n_cta;
+    const double w_big = std::max(share / 4.0, 8.0), w_small = std::max(share / 16.0, 4.0);       // >= 4 tiles (128 KB) per unit
     std::vector<SpUnit> units;
     std::vector<double> weight;
+    std::vector<int> chunk_splits(n_chunks, 0);
     size_t max_splits = 0;
     for (size_t R = 0; R < n_chunks; ++R) {
-        const size_t t_start = R * (TR / SPS_TC), row0 = R * TR;
-        size_t split = 0;
-        for (size_t t0 = t_start; t0 < n_tiles; t0 += tpu, ++split) {
-            const size_t t1 = std::min(n_tiles, t0 + tpu);
-            units.push_back(SpUnit{(int)R, (int)split, (int)t0, (int)t1});
-            // consumer cost, not bytes, is what a unit takes: a tile cut by the diagonal (or holding the last column) runs the
-            // masked path, measured ~3x the instructions of a dense tile (ncu, profiles/r01_spmv_stream_full.md)
+        const size_t t_start = R * (TR / SPS_TC);
+        double w_chunk = 0.0;
+        for (size_t t = t_start; t < n_tiles; ++t) w_chunk += tile_weight(R, t);
+        size_t split = 0, t0 = t_start;
+        double done = 0.0;
+        while (t0 < n_tiles) {
+            const double target = done < 0.75 * w_chunk ? w_big : w_small;
             double w = 0.0;
-            for (size_t t = t0; t < t1; ++t) {
-                const size_t ct = t * SPS_TC;
-                const bool dense = ct >= row0 + TR && ct + SPS_TC < n;
-                w += dense ? 1.0 : 3.0;
-            }
+            size_t t1 = t0;
+            while (t1 < n_tiles && t1 - t0 < (size_t)(SPS_MAX_UNIT_COLS / SPS_TC) && (w < target || t1 == t0)) { w += tile_weight(R, t1); ++t1; }
+            units.push_back(SpUnit{(int)R, (int)split, (int)t0, (int)t1});
             weight.push_back(w);
+            done += w;
+            t0 = t1;
+            ++split;
         }
+        chunk_splits[R] = (int)split;
         max_splits = std::max(max_splits, split);
     }
     const int grid = (int)std::min<size_t>(n_cta, units.size());
-    std::vector<int> cta_begin((size_t)grid + 1, 0);
-    double tot = 0.0;
-    for (double w : weight) tot += w;
-    double cum = 0.0;
-    size_t u = 0;
-    for (int b = 0; b < grid; ++b) {
-        cta_begin[(size_t)b] = (int)u;
-        const double target = tot * (double)(b + 1) / (double)grid;
-        while (u < units.size() && cum + 0.5 * weight[u] <= target) { cum += weight[u]; ++u; }
-    }
-    cta_begin[(size_t)grid] = (int)units.size();      // the last CTA takes whatever the midpoint rule left over
+    // heaviest first (stable: equal weights keep the chunk-major order, which streams the array front to back)
+    std::vector<size_t> order(units.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return weight[a] > weight[b]; });
+    std::vector<SpUnit> sorted(units.size());
+    for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
     SpPlan pl;
-    TB_CUDA(cudaMalloc(&pl.units_dev, units.size() * sizeof(SpUnit)));
-    TB_CUDA(cudaMalloc(&pl.cta_begin_dev, cta_begin.size() * sizeof(int)));
-    TB_CUDA(cudaMemcpy(pl.units_dev, units.data(), units.size() * sizeof(SpUnit), cudaMemcpyHostToDevice));
-    TB_CUDA(cudaMemcpy(pl.cta_begin_dev, cta_begin.data(), cta_begin.size() * sizeof(int), cudaMemcpyHostToDevice));
-    pl.grid = grid; pl.max_splits = (int)max_splits; pl.n_chunks = (int)n_chunks; pl.tiles_per_unit = (int)tpu;
+    TB_CUDA(cudaMalloc(&pl.units_dev, sorted.size() * sizeof(SpUnit)));
+    TB_CUDA(cudaMalloc(&pl.next_unit_dev, sizeof(int)));
+    TB_CUDA(cudaMemcpy(pl.units_dev, sorted.data(), sorted.size() * sizeof(SpUnit), cudaMemcpyHostToDevice));
+    TB_CUDA(cudaMemset(pl.next_unit_dev, 0, sizeof(int)));
+    TB_CUDA(cudaMalloc(&pl.chunk_splits_dev, chunk_splits.size() * sizeof(int)));
+    TB_CUDA(cudaMemcpy(pl.chunk_splits_dev, chunk_splits.data(), chunk_splits.size() * sizeof(int), cudaMemcpyHostToDevice));
+    pl.n_units = (int)sorted.size();
+    pl.grid = grid; pl.max_splits = (int)max_splits; pl.n_chunks = (int)n_chunks;
     return cache.emplace(n, pl).first->second;
 }
 
@@ -428,28 +492,37 @@ template <typename T> static void spmv_stream(size_t n, T alpha, const T* S, con
     const size_t total = n * (n + 1) / 2;
     size_t bytes_n = (size_t)pl.max_splits * n * sizeof(T);
     bytes_n = (bytes_n + 255) & ~size_t(255);
-    const size_t bytes_t = (size_t)pl.n_chunks * n * sizeof(T);
+    const int halves = g_spmv_halves;
+    const size_t bytes_t = (size_t)pl.n_chunks * halves * n * sizeof(T);
     char* sc = reinterpret_cast<char*>(scratch(bytes_n + bytes_t));
     SpParams p;
     p.S = S; p.n = n; p.total = total; p.x = x;
     p.part_n = sc; p.part_t = sc + bytes_n;
-    p.units = pl.units_dev; p.cta_begin = pl.cta_begin_dev;
+    p.units = pl.units_dev; p.n_units = pl.n_units; p.next_unit = pl.next_unit_dev;
     p.tail = (int)(total % VEC);
     const bool xres = n * sizeof(T) <= SPS_XRES_BYTES;
     const size_t stages = xres ? 5 : 6;
     const size_t x_elems = xres ? SPS_XRES_BYTES / sizeof(T) : (size_t)SPS_MAX_UNIT_COLS;
-    const size_t smem = stages * SPS_TC * (TR + VEC) * sizeof(T) + x_elems * sizeof(T) + 2 * stages * sizeof(uint64_t) + 128;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[xres ? 1 : 0]) {
-        if (xres) TB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else TB_CUDA(cudaFuncSetAttribute(spmv_stream_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[xres ? 1 : 0] = true;
+    const size_t smem = stages * SPS_TC * (TR + VEC) * sizeof(T) + x_elems * sizeof(T) + 2 * stages * sizeof(uint64_t) + (stages + 1) * 16 + 128;
+    auto launch = [&](auto kern, int threads) {
+        static std::map<const void*, bool> attr_set;           // one flag per kernel instantiation
+        const void* key = reinterpret_cast<const void*>(kern);
+        if (!attr_set[key]) {
+            TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[key] = true;
+        }
+        launch_pdl(kern, dim3(pl.grid), dim3(threads), smem, c.stream, p);
+    };
+    if (halves == 2) {
+        if (xres) launch(spmv_stream_kernel<T, true, 2>, SPS_CONSUMERS * 2 + 32);
+        else launch(spmv_stream_kernel<T, false, 2>, SPS_CONSUMERS * 2 + 32);
+    } else {
+        if (xres) launch(spmv_stream_kernel<T, true, 1>, SPS_THREADS);
+        else launch(spmv_stream_kernel<T, false, 1>, SPS_THREADS);
     }
-    if (xres) spmv_stream_kernel<T, true><<<pl.grid, SPS_THREADS, smem, c.stream>>>(p);
-    else spmv_stream_kernel<T, false><<<pl.grid, SPS_THREADS, smem, c.stream>>>(p);
     TB_LAUNCH_CHECK();
-    spmv_stream_finalize<T><<<(unsigned)((n + 31) / 32), 256, 0, c.stream>>>(reinterpret_cast<const T*>(p.part_n), reinterpret_cast<const T*>(p.part_t), S, x,
-                                                                              n, total, p.tail, pl.tiles_per_unit, alpha, beta, y);
+    launch_pdl(spmv_stream_finalize<T>, dim3((unsigned)((n + 31) / 32)), dim3(256), 0, c.stream, reinterpret_cast<const T*>(p.part_n), reinterpret_cast<const T*>(p.part_t), S, x,
+               n, total, p.tail, (const int*)pl.chunk_splits_dev, halves, alpha, beta, y, pl.next_unit_dev);
     TB_LAUNCH_CHECK();
 }
 
@@ -482,6 +555,12 @@ template <typename T> static void api_transform_sp(size_t n, T alpha, tb_view ma
 
 using namespace tb;
 extern "C" {
+int tb_set_spmv_warps(int warps) {
+    return api([&] {
+        TB_REQUIRE(warps == 8 || warps == 16, "spmv consumer warps: 8 or 16");
+        g_spmv_halves = warps / 8;
+    });
+}
 int tb_transform_sp_f32(size_t n, float a, tb_view m, tb_view x, float b, tb_view y) { return api_defer({m, x, y}, {y}, [=] { api_transform_sp<float>(n, a, m, x, b, y); }); }
 int tb_transform_sp_f64(size_t n, double a, tb_view m, tb_view x, double b, tb_view y) { return api_defer({m, x, y}, {y}, [=] { api_transform_sp<double>(n, a, m, x, b, y); }); }
 }
