@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--repeats", type=int, default=5, help="timed windows of --steps iterations each; the median window is reported")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timeline", default=None, help="write the device timeline of 3 extra iterations to this path (diagnostics; see scripts/timeline_summary.py)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity leg (x_hat / y_hat vs the f64 oracle on the timed workload)")
     ap.add_argument("--parity-k", type=int, default=10, help="largest iteration count of the parity leg: K in {1, 10} (+ 100 when >= 100)")
     ap.add_argument("--cpu-sample-blocks", type=int, default=None)
@@ -609,6 +610,18 @@ def main():
     v_l, v_ms, v_b = (C.c_uint64 * 9)(), (C.c_double * 9)(), (C.c_double * 9)()
     capi.check(L.tb_prof_read_variants(v_l, v_ms, v_b))
     capi.check(L.tb_prof_enable(0))
+    if args.timeline:
+        # real device timeline of 3 iterations (csrc/context.cu tb_timeline_*): one line per launch, completion time on the
+        # device and issue time on the host; written by every rank next to each other (PATH.rank<r>)
+        capi.check(L.tb_timeline_begin(8192))
+        s.step(3)
+        capi.check(L.tb_flush())
+        need = C.c_size_t()
+        capi.check(L.tb_timeline_dump(None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value + 16)
+        capi.check(L.tb_timeline_dump(buf, len(buf), C.byref(need)))
+        with open(args.timeline + (".rank%d" % rank if world > 1 else ""), "w") as f:
+            f.write(buf.value.decode())
     s.close()
 
     # ---- end to end: one whole Solver::solve through the public API with host buffers (work, c, b - and for the QP

@@ -79,6 +79,9 @@ int         tb_pairs_fused(uint64_t* out);           /* pairs served by one pass
  * tb_vprog_stats: programs launched / micro-ops recorded since tb_init. */
 int         tb_set_vprog(int on);
 int         tb_vprog_stats(uint64_t* launches, uint64_t* ops);
+/* longest vector (elements) a barrier-capable cluster program takes; longer ones go to barrier-free full-grid programs that are
+ * cut at every hazard.  Default 49152 (env TB_VPROG_MAX_N); diagnostics / A-B only. */
+int         tb_set_vprog_max_n(size_t n);
 int         tb_flush(void);
 /* Speculative pairing (csrc/gemv.cu): while one op/trans_op pair streams A, the two products of the pair that followed
  * it last time are computed from the same staged tiles and parked; when that pair arrives it is served by the finalize
@@ -101,6 +104,12 @@ int         tb_host_wait_stats(double* seconds, uint64_t* waits);
  * seconds per entry point; tb_api_trace_dump writes "name calls seconds\n" lines into buf (needed = bytes required). */
 int         tb_set_api_trace(int on);
 int         tb_api_trace_dump(char* buf, size_t cap, size_t* needed);
+/* Device timeline (diagnostics): after tb_timeline_begin(max_events) every kernel launch of the library records a CUDA event
+ * behind it; tb_timeline_dump writes "index file:line device_us host_us\n" per launch (device_us = completion time of that
+ * kernel, host_us = when the launch call was made, both relative to the first launch) and stops recording.  Shows one solver
+ * iteration kernel by kernel with its real gaps (PDL overlap, host round trips, peer waits) without a serialising profiler. */
+int         tb_timeline_begin(size_t max_events);
+int         tb_timeline_dump(char* buf, size_t cap, size_t* needed);
 
 /* ---- buffers: the SliceLike role (slicelike.rs:23-69; totsu_f32cuda/src/f32cuda_slice.rs:215-309) ------- */
 /* SliceLike::new_ref / new_mut: wrap caller-owned host memory with a device mirror.  The host slice stays

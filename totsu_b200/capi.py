@@ -59,7 +59,8 @@ def _signatures():
         "tb_set_speculation": (i, [i]), "tb_spec_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "tb_set_scalar_prefetch": (i, [i]), "tb_scalar_prefetch_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "tb_set_api_trace": (i, [i]), "tb_api_trace_dump": (i, [C.c_char_p, sz, C.POINTER(sz)]),
-        "tb_set_vprog": (i, [i]), "tb_vprog_stats": (i, [C.POINTER(u64), C.POINTER(u64)]), "tb_flush": (i, []),
+        "tb_timeline_begin": (i, [sz]), "tb_timeline_dump": (i, [C.c_char_p, sz, C.POINTER(sz)]),
+        "tb_set_vprog": (i, [i]), "tb_set_vprog_max_n": (i, [sz]), "tb_vprog_stats": (i, [C.POINTER(u64), C.POINTER(u64)]), "tb_flush": (i, []),
         "tb_prof_enable": (i, [i]), "tb_prof_read": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "tb_prof_read_variants": (i, [C.POINTER(u64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "tb_buf_wrap": (i, [i, vp, sz, i, C.POINTER(H)]), "tb_buf_alloc": (i, [i, sz, C.POINTER(H)]),

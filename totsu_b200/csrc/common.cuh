@@ -160,6 +160,13 @@ struct Context {
     // slab for tiny buffers (the solver wraps a 1-element slice every iteration: solver.rs:590-591)
     char* small_slab = nullptr;
     std::vector<int> small_free;
+    // Released device blocks kept for the next buffer of the same (256-byte rounded) size: every Solver::solve wraps its `work`
+    // slice anew (solver.rs:315) and drops it at the end, and cudaMalloc / cudaFree are the two calls of that sequence that
+    // serialise with everything else in the driver (measured: 1-250 ms stalls of begin / end when a monitoring tool polls the
+    // GPU).  Blocks above kPoolMaxBlock (the matrices) are returned to the driver as before.
+    static constexpr size_t kPoolMaxBlock = size_t(256) << 20, kPoolMaxBytes = size_t(1) << 30;
+    std::multimap<size_t, char*> pool;
+    size_t pool_bytes = 0;
     static constexpr size_t kSmallBytes = 256;
     static constexpr int kSmallSlots = 1024;
     uint64_t launches = 0;
@@ -249,10 +256,16 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.numAttrs = na;
     TB_CUDA(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
-#define TB_LAUNCH_CHECK()                   \
-    do {                                    \
-        TB_CUDA(cudaGetLastError());        \
-        ::tb::count_launch();               \
+// Device timeline (tb_timeline_begin / tb_timeline_dump): with it on, every launch site records a CUDA event behind its kernel
+// and the host time of the launch call, so one solver iteration can be laid out kernel by kernel with its real gaps - under the
+// real overlap (PDL, host round trips, peer waits), which a serialising profiler cannot show.  Off: one predictable branch.
+extern bool g_timeline_on;
+void timeline_mark(const char* file, int line);
+#define TB_LAUNCH_CHECK()                                                       \
+    do {                                                                        \
+        TB_CUDA(cudaGetLastError());                                            \
+        ::tb::count_launch();                                                   \
+        if (::tb::g_timeline_on) ::tb::timeline_mark(__FILE__, __LINE__);       \
     } while (0)
 
 // A parked cone projection (cone.cu: the first of the two projections of an iteration waits for its partner) runs before

@@ -42,6 +42,22 @@ ApiScope::~ApiScope() {
     }
     if (g_nvtx) nvtxRangePop();
 }
+// ---- device timeline ------------------------------------------------------------------------------------------
+bool g_timeline_on = false;
+namespace {
+struct TimelineEntry { const char* file; int line; cudaEvent_t ev; double host_s; };
+std::vector<TimelineEntry> g_timeline;
+std::vector<cudaEvent_t> g_timeline_pool;
+size_t g_timeline_cap = 0;
+}  // namespace
+void timeline_mark(const char* file, int line) {
+    if (g_timeline.size() >= g_timeline_cap) return;
+    cudaEvent_t ev = g_timeline_pool[g_timeline.size()];
+    if (cudaEventRecord(ev, g_ctx.stream.raw) != cudaSuccess) return;
+    const char* base = file;
+    for (const char* p = file; *p; ++p) if (*p == '/') base = p + 1;
+    g_timeline.push_back(TimelineEntry{base, line, ev, std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count()});
+}
 static int g_pdl = -1;
 bool pdl_enabled() {
     if (g_pdl < 0) {
@@ -183,8 +199,35 @@ static void alloc_dev(Buffer& b) {
         b.dev = c.small_slab + (size_t)b.small_slot * Context::kSmallBytes;
     } else {
         b.small_slot = -1;
-        TB_CUDA(cudaMalloc(&b.dev, std::max<size_t>(bytes, 16)));
+        const size_t rounded = (std::max<size_t>(bytes, 16) + 255) & ~size_t(255);
+        auto it = c.pool.find(rounded);
+        if (it != c.pool.end()) {
+            b.dev = it->second;
+            c.pool.erase(it);
+            c.pool_bytes -= rounded;
+        } else {
+            TB_CUDA(cudaMalloc(&b.dev, rounded));
+        }
     }
+}
+
+// give a device block back: to the pool when it is small enough to be worth keeping, else to the driver.  The caller has
+// drained the stream (nothing in flight still touches the block).
+static void free_dev(char* dev, size_t bytes) {
+    Context& c = ctx();
+    const size_t rounded = (std::max<size_t>(bytes, 16) + 255) & ~size_t(255);
+    if (rounded <= Context::kPoolMaxBlock) {
+        while (c.pool_bytes + rounded > Context::kPoolMaxBytes && !c.pool.empty()) {
+            auto big = std::prev(c.pool.end());
+            cudaFree(big->second);
+            c.pool_bytes -= big->first;
+            c.pool.erase(big);
+        }
+        c.pool.emplace(rounded, dev);
+        c.pool_bytes += rounded;
+        return;
+    }
+    TB_CUDA(cudaFree(dev));
 }
 
 static void host_sync_range(Buffer& b, size_t off, size_t len) {
@@ -302,6 +345,7 @@ int tb_init(int device) {
         (void)scratch(size_t(8) << 20);
         c.launches = 0;
         if (const char* e = std::getenv("TB_NVTX")) g_nvtx = std::atoi(e) != 0;
+        if (const char* e = std::getenv("TB_VPROG_MAX_N")) { const long v = std::atol(e); if (v >= 1024 && v <= (1l << 22)) vp_set_max_n((size_t)v); }
         c.inited = true;
     });
 }
@@ -318,6 +362,9 @@ int tb_shutdown(void) {
         c.bufs.clear();
         c.free_ids.clear();
         c.host_index.clear();
+        for (auto& e : c.pool) cudaFree(e.second);
+        c.pool.clear();
+        c.pool_bytes = 0;
         if (c.scratch) cudaFree(c.scratch);
         c.scratch = nullptr;
         c.scratch_bytes = 0;
@@ -373,6 +420,13 @@ int tb_set_vprog(int on) {
         ctx().vprog = on != 0;
     });
 }
+int tb_set_vprog_max_n(size_t n) {
+    return api([&] {
+        require_init();
+        TB_REQUIRE(n >= 1024 && n <= (size_t(1) << 22), "vprog max n: 1024 .. 4M elements");
+        vp_set_max_n(n);
+    });
+}
 int tb_vprog_stats(uint64_t* launches, uint64_t* ops) {
     return api_raw([&] { *launches = ctx().vprog_launches; *ops = ctx().vprog_ops; });
 }
@@ -398,6 +452,45 @@ int tb_host_wait_stats(double* seconds, uint64_t* waits) {
         ctx().box_wait_s = 0.0; ctx().box_waits = 0;
     });
 }
+int tb_timeline_begin(size_t max_events) {
+    return api([&] {
+        require_init();
+        TB_CUDA(cudaStreamSynchronize(ctx().stream));
+        g_timeline.clear();
+        while (g_timeline_pool.size() < max_events) {
+            cudaEvent_t ev;
+            TB_CUDA(cudaEventCreate(&ev));
+            g_timeline_pool.push_back(ev);
+        }
+        g_timeline_cap = max_events;
+        g_timeline_on = max_events > 0;
+    });
+}
+// "index file:line device_us host_us" per launch since tb_timeline_begin, both clocks relative to the first launch; the device
+// time of a launch is the completion time of its kernel.  Stops recording.
+int tb_timeline_dump(char* buf, size_t cap, size_t* needed) {
+    return api([&] {
+        require_init();
+        g_timeline_on = false;
+        TB_CUDA(cudaStreamSynchronize(ctx().stream));
+        std::string out;
+        char line[160];
+        for (size_t i = 0; i < g_timeline.size(); ++i) {
+            float ms = 0.f;
+            TB_CUDA(cudaEventElapsedTime(&ms, g_timeline[0].ev, g_timeline[i].ev));
+            std::snprintf(line, sizeof line, "%zu %s:%d %.3f %.3f\n", i, g_timeline[i].file, g_timeline[i].line, (double)ms * 1e3,
+                          (g_timeline[i].host_s - g_timeline[0].host_s) * 1e6);
+            out += line;
+        }
+        if (needed) *needed = out.size() + 1;
+        if (buf && cap > 0) {
+            const size_t nb = std::min(cap - 1, out.size());
+            std::memcpy(buf, out.data(), nb);
+            buf[nb] = 0;
+        }
+    });
+}
+
 int tb_set_api_trace(int on) {
     return api_keep_pending([&] {
         g_api_trace = on != 0;
@@ -548,7 +641,7 @@ int tb_buf_release(tb_handle h) {
             c.small_free.push_back(b.small_slot);
         } else if (b.dev) {
             TB_CUDA(cudaStreamSynchronize(c.stream));
-            TB_CUDA(cudaFree(b.dev));
+            free_dev(b.dev, b.len * b.esize);
         }
         b = Buffer();
         c.free_ids.push_back(h);

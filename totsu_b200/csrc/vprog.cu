@@ -35,7 +35,13 @@ constexpr int VP_THREADS = 1024;
 constexpr int VP_MAX_OPS = 44;
 constexpr int VP_SLOTS = 32;            // reduction slots of VP_MAX_CTAS doubles each
 constexpr int VP_MAX_CTAS = VP_CLUSTER;
-constexpr size_t VP_MAX_N = 49152;      // longest vector worth running on one cluster of 8 SMs
+// Longest vector run on one cluster of 8 SMs.  Measured on B200 (scripts/bench_vprog_stage.py, profiles/r02_vprog_threshold.md):
+// a barrier-separated stage costs 1.3 us up to 64 K elements but 3.5 us at 147 K (8 SMs pull only ~0.4 TB/s out of L2), while a
+// barrier-free wide program pays a launch boundary (3-5 us with PDL) at every hazard.  Raising the threshold to 256 K takes C3's
+// iteration from 24 launches to 14 and makes it SLOWER (1.447 -> 1.540 ms; C4 0.929 -> 1.027): 48 K stays.
+// tb_set_vprog_max_n / TB_VPROG_MAX_N change it (diagnostics).
+size_t g_vp_max_n = 49152;
+#define VP_MAX_N g_vp_max_n
 constexpr size_t VP_WIDE_MAX_N = size_t(1) << 22;    // beyond this a dedicated kernel with a larger grid is the better tool
 
 enum : uint8_t {
@@ -301,6 +307,7 @@ Range slot_range(int slot) { return range_of(g_rec.slots + (size_t)slot * VP_MAX
 }  // namespace
 
 bool vp_enabled(size_t n) { return ctx().vprog && n <= VP_MAX_N; }
+void vp_set_max_n(size_t n) { vp_flush(); g_vp_max_n = n; }
 // element-wise ops of any practical length can be recorded: beyond VP_MAX_N the program becomes a barrier-free "wide" one
 bool vp_enabled_wide(size_t n) { return ctx().vprog && n <= VP_WIDE_MAX_N; }
 
@@ -324,6 +331,7 @@ void vp_flush() {
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaErrorLaunchFailure;
     }
+    if (g_timeline_on) timeline_mark(R.wide ? "vprog_wide#ops" : "vprog_cluster#ops", R.prog.n_ops);
     R.prog.n_ops = 0;
     R.next_slot = 0;
     R.wide = false; R.has_barrier = false; R.has_reduction = false; R.max_n = 0;

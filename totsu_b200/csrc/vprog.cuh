@@ -7,6 +7,7 @@ namespace tb {
 
 bool vp_enabled_wide(size_t n);   // element-wise ops: any length up to 4M elements (long ones make the program a barrier-free wide one)
 bool vp_enabled(size_t n = 1);      // recording is on and a vector of n elements is short enough for the cluster executor
+void vp_set_max_n(size_t n);     // longest vector a cluster program takes (flushes the pending program)
 void vp_init();
 void vp_shutdown();
 void vp_fill(int dtype, void* y, double v, size_t n);
