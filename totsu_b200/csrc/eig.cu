@@ -365,6 +365,20 @@ static char* eig_scratch(size_t bytes) {
     return c.eig_scratch;
 }
 
+// f32 schedule of the sign iteration: n1 quintic steps (3 GEMMs each) then n2 Newton-Schulz steps (2 GEMMs each).
+// TB_PSD_STEPS="n1,n2" overrides it (diagnostics: scripts/psd_schedule.py measures error and time per schedule).
+static void psd_schedule_f32(int& n1, int& n2) {
+    static int s1 = -1, s2 = -1;
+    if (s1 < 0) {
+        s1 = 10; s2 = 8;
+        if (const char* e = std::getenv("TB_PSD_STEPS")) {
+            int a = 0, b = 0;
+            if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 40 && b >= 0 && b <= 40) { s1 = a; s2 = b; }
+        }
+    }
+    n1 = s1; n2 = s2;
+}
+
 template <typename T> static void psd_project_sign(T* x, size_t k, T* work) {
     Context& c = ctx();
     const size_t kk = k * k;
@@ -380,7 +394,8 @@ template <typename T> static void psd_project_sign(T* x, size_t k, T* work) {
     l1_sumsq_async<T>(X, kk, sumsq);
     scale_inv_norm_kernel<T><<<std::min<unsigned>(gkk, 4096u), 256, 0, c.stream>>>(X, S0, kk, sumsq);
     TB_LAUNCH_CHECK();
-    const int n1 = sizeof(T) == 4 ? 10 : 24, n2 = sizeof(T) == 4 ? 8 : 12;
+    int n1 = 24, n2 = 12;
+    if (sizeof(T) == 4) psd_schedule_f32(n1, n2);
     const T qa = (T)3.4445, qb = (T)-4.7750, qc = (T)2.0315;
     T* S = S0; T* Sn = S1;
     // psd_mode 0: tensor cores where they apply (f32, k >= 64, k % 4 == 0); 2: FP32/FP64-pipe GEMM; 3: tensor cores without split-K
@@ -431,7 +446,8 @@ void psd_project_pair(float* x0, float* x1, size_t sn, float* work, size_t work_
         scale_inv_norm_kernel<float><<<std::min<unsigned>(gkk, 4096u), 256, 0, c.stream>>>(X[i], S0[i], kk, sumsq);
         TB_LAUNCH_CHECK();
     }
-    const int n1 = 10, n2 = 8;                                  // same schedule as psd_project_sign<float>
+    int n1, n2;
+    psd_schedule_f32(n1, n2);                                   // same schedule as psd_project_sign<float>
     const float qa = 3.4445f, qb = -4.7750f, qc = 2.0315f;
     const float* nul[2] = {nullptr, nullptr};
     float* S[2] = {S0[0], S0[1]};
