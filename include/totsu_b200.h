@@ -192,12 +192,13 @@ int tb_symm_gemm_f32(size_t k, float alpha, tb_view a, tb_view b, float beta, tb
  * at its phases into stamps_ns[0..8]: entered, prologue done, dependency resolved, first chunk staged, producers
  * done, accumulator complete, partials pushed, cluster barrier passed, results stored. */
 int tb_symm_gemm_trace_f32(size_t k, tb_view a, tb_view b, tb_view c, int splitk, int reps, uint64_t* stamps_ns);
-/* The two tb_cone_proj_f32 calls of one solver iteration (dual cone on y, primal cone on s) on a cone with PSD blocks are
- * batched: the first is parked until the second arrives (or anything else is called) and every GEMM of the sign
- * iteration then covers both problems in one launch.  tb_set_psd_pairing(0) runs each call at once; tb_psd_pairs counts
- * batched block pairs. */
+/* The two tb_cone_proj calls of one solver iteration (dual cone on y, primal cone on s: solver.rs:548-549) are batched: the
+ * first is parked until the second arrives (or anything else is called); the Zero / RPos / SOC / RotSOC blocks of both vectors then
+ * run as one launch and, in f32, every GEMM of the PSD sign iteration covers both problems.  tb_set_psd_pairing(0) runs each call
+ * at once; tb_psd_pairs counts batched PSD block pairs, tb_cone_pairs the projection pairs served by one launch. */
 int tb_set_psd_pairing(int on);
 int tb_psd_pairs(uint64_t* out);
+int tb_cone_pairs(uint64_t* out);
 int tb_proj_psd_f32(tb_view x, float eps_zero, tb_view work);
 /* MatBuild::set_sqrt (totsu/src/matbuild/mod.rs:220-241): mat := P^(1/2) for an upper-packed symmetric PSD P, i.e. map_eig with
  * scale_diag = None and the closure e -> sqrt(e) on the positive eigenvalues - GEMM-only (coupled Newton-Schulz on the

@@ -275,6 +275,61 @@ def test_proj_psd_c4_full_size(dt):
     ip = float(np.dot(x.astype(np.float64), neg.astype(np.float64)))
     assert abs(ip) <= 50 * tol * float(np.dot(x.astype(np.float64), x.astype(np.float64)))
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_cone_proj_pair_is_one_launch_and_bit_identical(dt, case):
+    """The two projections of an iteration (dual cone on y, primal cone on s: solver.rs:548-549) on a product cone WITHOUT PSD
+    blocks: the first call is parked and both vectors are projected by one cone_kernel launch (tb_cone_pairs counts it, the
+    launch counter sees one launch instead of two); bit-identical to the two separate launches (same code per block), equal to
+    the oracle; an unpairable second call (overlapping vector) and a lone call are still served in program order."""
+    import ctypes as C
+    L = capi.lib()
+    blocks = CASES[case]
+    m = sum(l for _, l in blocks)
+    rng = np.random.default_rng(100 + case)
+    y0, s0 = rng.standard_normal(m).astype(dt), rng.standard_normal(m).astype(dt)
+    want = []
+    for v, dual in ((y0, True), (s0, False)):
+        w = v.astype(np.float64).copy()
+        oracle_cone(blocks).proj(dual, w)
+        want.append(w)
+    h = _cone(blocks)
+    f = capi.fn("tb_cone_proj", dt)
+    none = capi.View(0, 0, 0)
+    res, launches = {}, {}
+    for pairing in (1, 0):
+        capi.check(L.tb_set_psd_pairing(pairing))
+        buf = np.concatenate([y0, s0]).copy()
+        vb = capi.Buf(buf)
+        capi.check(L.tb_flush())
+        n0, n1, l0, l1 = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        capi.check(L.tb_cone_pairs(C.byref(n0))); capi.check(L.tb_launch_count(C.byref(l0)))
+        capi.check(f(h, 1, vb.view(0, m), 1e-12, none))
+        capi.check(f(h, 0, vb.view(m, m), 1e-12, none))
+        capi.check(L.tb_flush())
+        capi.check(L.tb_cone_pairs(C.byref(n1))); capi.check(L.tb_launch_count(C.byref(l1)))
+        vb.release()
+        assert n1.value - n0.value == (1 if pairing else 0)
+        launches[pairing] = l1.value - l0.value          # cone launches + whatever the uploads of the two views took
+        res[pairing] = buf
+        tol = 5e-6 if dt == np.float32 else 1e-12
+        for i in range(2):
+            assert rel_linf(buf[i * m:(i + 1) * m], want[i]) <= tol, (pairing, i)
+    capi.check(L.tb_set_psd_pairing(1))
+    assert np.array_equal(res[1], res[0])
+    assert launches[1] == launches[0] - 1, launches
+    # the second call overlaps the first one's vector: not pairable, both run in program order (proj of proj = proj on K, then K*)
+    twice = y0.copy()
+    vb = capi.Buf(twice)
+    capi.check(f(h, 0, vb.view(), 1e-12, none))
+    capi.check(f(h, 0, vb.view(), 1e-12, none))
+    vb.release()
+    w = y0.astype(np.float64).copy()
+    oracle_cone(blocks).proj(False, w)
+    oracle_cone(blocks).proj(False, w)
+    assert rel_linf(twice, w) <= (5e-6 if dt == np.float32 else 1e-12)
+    capi.check(L.tb_cone_destroy(h))
+
 
 # ---- tcgen05 engine of the sign iteration (csrc/psd_tc.cu) -------------------------------------------------
 def _sym32(rng, k):

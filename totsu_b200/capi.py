@@ -55,7 +55,7 @@ def _signatures():
         "tb_launch_count": (i, [C.POINTER(u64)]), "tb_set_gemv_path": (i, [i]), "tb_set_pdl": (i, [i]), "tb_set_spmv_warps": (i, [i]), "tb_set_psd_path": (i, [i]),
         "tb_set_pair_fusion": (i, [i]), "tb_pairs_fused": (i, [C.POINTER(u64)]),
         "tb_host_wait_stats": (i, [C.POINTER(C.c_double), C.POINTER(u64)]),
-        "tb_set_psd_pairing": (i, [i]), "tb_psd_pairs": (i, [C.POINTER(u64)]),
+        "tb_set_psd_pairing": (i, [i]), "tb_psd_pairs": (i, [C.POINTER(u64)]), "tb_cone_pairs": (i, [C.POINTER(u64)]),
         "tb_set_speculation": (i, [i]), "tb_spec_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "tb_set_scalar_prefetch": (i, [i]), "tb_scalar_prefetch_stats": (i, [C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "tb_set_api_trace": (i, [i]), "tb_api_trace_dump": (i, [C.c_char_p, sz, C.POINTER(sz)]),

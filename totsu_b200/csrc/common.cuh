@@ -178,6 +178,8 @@ struct Context {
     int gemv_mode = 0;
     bool psd_pairing = true;             // park the first ConePSD projection of an iteration and batch it with the second (cone.cu)
     uint64_t psd_pairs = 0;
+    uint64_t cone_pairs = 0;
+    uint64_t sets_skipped = 0;        // tb_set1 calls that wrote back the value both copies already held          // pairs of projections served by one cone_kernel launch
     int psd_mode = 0;                    // 0: matrix-sign iteration (tcgen05 GEMMs for f32), 1: Jacobi eigendecomposition, 2: sign on FP32/FP64 pipes, 3: tcgen05 without split-K
     char* eig_scratch = nullptr;         // 3 k*k matrices for the sign iteration
     size_t eig_scratch_bytes = 0;
@@ -225,6 +227,9 @@ template <typename T> struct DT;
 template <> struct DT<float> { static constexpr int id = TB_F32; };
 template <> struct DT<double> { static constexpr int id = TB_F64; };
 
+// A 1-element operand whose host copy is current (the solver wraps `work_one = [1]` anew every iteration and applies the n x 1
+// operators b and c to it, solver.rs:590-596): its value can travel by value instead of being uploaded and read back on the device.
+bool host_scalar_if_current(const tb_view& x, int dtype, double* out);
 template <typename T> inline const T* rptr(const tb_view& v) { return reinterpret_cast<const T*>(dev_ptr(v, DT<T>::id, false)); }
 template <typename T> inline T* wptr(const tb_view& v, bool full_overwrite = false) { return reinterpret_cast<T*>(dev_ptr(v, DT<T>::id, true, full_overwrite)); }
 
@@ -340,6 +345,7 @@ void spec_note_release(tb_handle buf);
 void spec_reset();
 // scalar prefetch hooks (prefetch.cu): reductions that followed a host-visible request last time ride on its round trip
 void pf_before_wait();
+void pf_into_program();        // the same reductions recorded into the pending vector program instead (one launch fewer, no latency chain of their own)
 void pf_note_write(tb_handle buf, size_t off, size_t len);
 void pf_note_release(tb_handle buf);
 void pf_reset();

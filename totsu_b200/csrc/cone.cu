@@ -93,10 +93,15 @@ __device__ __forceinline__ void soc_block(T* x, unsigned long long len, int type
     }
 }
 
+// blockIdx.y selects the vector: the two projections of one solver iteration (y block onto K*, s block onto K,
+// solver.rs:548-549) run as ONE launch over the same item table (gridDim.y = 2); a single projection has gridDim.y = 1.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(CN_THREADS) cone_kernel(T* x, const ConeItem* __restrict__ items, const SmallBlock* __restrict__ small, int dual_cone) {
+__global__ void __launch_bounds__(CN_THREADS) cone_kernel(T* x0, const ConeItem* __restrict__ items, const SmallBlock* __restrict__ small, int dual0,
+                                                          T* x1 = nullptr, int dual1 = 0) {
     __shared__ double red[32];
     tbd::pdl_entry();
+    T* x = blockIdx.y == 0 ? x0 : x1;
+    const int dual_cone = blockIdx.y == 0 ? dual0 : dual1;
     const ConeItem it = items[blockIdx.x];
     if (it.kind == 0) {
         if (MODE == 1) return;                                 // Zero / RPos: product_group does nothing
@@ -213,7 +218,8 @@ template <typename T> static void cone_proj(tb_handle h, int dual_cone, tb_view 
     T* px = wptr<T>(x);
     Context& c = ctx();
     if (cs.has_work) {
-        launch_pdl(cone_kernel<T, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, dual_cone);
+        launch_pdl(cone_kernel<T, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, dual_cone,
+                   (T*)nullptr, 0);
         TB_LAUNCH_CHECK();
     }
     if (cs.has_psd) {
@@ -229,15 +235,17 @@ template <typename T> static void cone_proj(tb_handle h, int dual_cone, tb_view 
 }
 
 // ---- pairing of the two projections of one iteration ----------------------------------------------------------
-// The solver projects the y block onto K* and the s block onto K back to back (solver.rs:548-549).  For a cone with PSD
-// blocks in f32 the first call is parked; when the second arrives (same cone, disjoint vector, same work buffer) the PSD
-// blocks of both run as ONE batch on the tensor cores (eig.cu:psd_project_pair).  Any other API call runs the parked
-// projection first (api_raw checks g_cone_pending), so program order is preserved.
+// The solver projects the y block onto K* and the s block onto K back to back (solver.rs:548-549).  The first call is parked;
+// when the second arrives (same cone, same element type, disjoint vector, same work buffer) both run together: the
+// Zero / RPos / SOC / RotSOC blocks of both vectors in ONE cone_kernel launch (gridDim.y = 2), the PSD blocks of both (f32) as
+// ONE batch on the tensor cores (eig.cu:psd_project_pair).  Any other API call runs the parked projection first (api_raw checks
+// g_cone_pending), so program order is preserved; arguments are validated before parking.  tb_set_psd_pairing(0) turns it off.
 struct PendingProj {
     tb_handle h = 0;
     int dual = 0;
+    int dtype = TB_F32;
     tb_view x{0, 0, 0}, w{0, 0, 0};
-    float eps = 0.f;
+    double eps = 0.0;
 };
 static PendingProj g_pending;
 bool g_cone_pending = false;
@@ -246,63 +254,75 @@ void cone_flush_pending() {
     if (!g_cone_pending) return;
     g_cone_pending = false;
     const PendingProj p = g_pending;
-    cone_proj<float>(p.h, p.dual, p.x, p.eps, p.w);
+    if (p.dtype == TB_F32) cone_proj<float>(p.h, p.dual, p.x, (float)p.eps, p.w);
+    else cone_proj<double>(p.h, p.dual, p.x, p.eps, p.w);
+}
+
+static void cone_flush_one(const PendingProj& p) {
+    if (p.dtype == TB_F32) cone_proj<float>(p.h, p.dual, p.x, (float)p.eps, p.w);
+    else cone_proj<double>(p.h, p.dual, p.x, p.eps, p.w);
 }
 
 static bool views_disjoint(const tb_view& a, const tb_view& b) {
     return a.buf != b.buf || a.off + a.len <= b.off || b.off + b.len <= a.off;
 }
 
-// both projections at once: non-PSD blocks through cone_kernel per vector, PSD blocks pairwise batched
-static void cone_proj_pair(const PendingProj& p0, tb_handle h, int dual1, tb_view x1, float eps1, tb_view w) {
+// both projections at once
+template <typename T> static void cone_proj_pair(const PendingProj& p0, tb_handle h, int dual1, tb_view x1, T eps1, tb_view w) {
     ConeSet& cs = get_cone(h);
     Context& c = ctx();
-    float* px0 = wptr<float>(p0.x);
-    float* px1 = wptr<float>(x1);
-    float* pw = wptr<float>(w);
+    T* px0 = wptr<T>(p0.x);
+    T* px1 = wptr<T>(x1);
     if (cs.has_work) {
-        launch_pdl(cone_kernel<float, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px0, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, p0.dual);
+        launch_pdl(cone_kernel<T, 0>, dim3(cs.n_items, 2), dim3(CN_THREADS), 0, c.stream, px0, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, p0.dual,
+                   px1, dual1);
         TB_LAUNCH_CHECK();
-        launch_pdl(cone_kernel<float, 0>, dim3(cs.n_items), dim3(CN_THREADS), 0, c.stream, px1, (const ConeItem*)cs.d_items, (const SmallBlock*)cs.d_small, dual1);
-        TB_LAUNCH_CHECK();
+        c.cone_pairs += 1;
     }
+    if (!cs.has_psd) return;
+    T* pw = wptr<T>(w);
     size_t off = 0;
     for (const tb_cone_block& b : cs.blocks) {
         if (b.type == TB_CONE_PSD && b.len > 0) {
-            if (psd_pair_usable((size_t)b.len, pw) && ((reinterpret_cast<uintptr_t>(px0 + off) | reinterpret_cast<uintptr_t>(px1 + off)) & 3u) == 0) {
-                psd_project_pair(px0 + off, px1 + off, (size_t)b.len, pw, w.len);
-                c.psd_pairs += 1;
-            } else {
-                psd_project<float>(px0 + off, (size_t)b.len, p0.eps, pw, w.len);
-                psd_project<float>(px1 + off, (size_t)b.len, eps1, pw, w.len);
+            bool batched = false;
+            if constexpr (sizeof(T) == 4) {
+                if (c.psd_mode == 0 && psd_pair_usable((size_t)b.len, pw) && ((reinterpret_cast<uintptr_t>(px0 + off) | reinterpret_cast<uintptr_t>(px1 + off)) & 3u) == 0) {
+                    psd_project_pair(px0 + off, px1 + off, (size_t)b.len, pw, w.len);
+                    c.psd_pairs += 1;
+                    batched = true;
+                }
+            }
+            if (!batched) {
+                psd_project<T>(px0 + off, (size_t)b.len, (T)p0.eps, pw, w.len);
+                psd_project<T>(px1 + off, (size_t)b.len, eps1, pw, w.len);
             }
         }
         off += (size_t)b.len;
     }
 }
 
-static void cone_proj_submit_f32(tb_handle h, int dual, tb_view x, float eps, tb_view w) {
+template <typename T> static void cone_proj_submit(tb_handle h, int dual, tb_view x, T eps, tb_view w) {
     require_init();
     if (!ctx().queue.empty()) queue_drain();
     ConeSet& cs = get_cone(h);
-    cone_validate<float>(cs, x, w);
+    cone_validate<T>(cs, x, w);
     if (g_cone_pending) {
         const PendingProj p0 = g_pending;
-        const bool pairable = p0.h == h && views_disjoint(p0.x, x) && p0.w.buf == w.buf && p0.w.off == w.off && p0.w.len == w.len &&
-                              views_disjoint(p0.x, w) && views_disjoint(x, w);
+        const bool pairable = p0.h == h && p0.dtype == DT<T>::id && views_disjoint(p0.x, x) && p0.w.buf == w.buf && p0.w.off == w.off && p0.w.len == w.len &&
+                              (w.len == 0 || (views_disjoint(p0.x, w) && views_disjoint(x, w)));
         g_cone_pending = false;
         if (pairable) {
-            cone_proj_pair(p0, h, dual, x, eps, w);
+            cone_proj_pair<T>(p0, h, dual, x, eps, w);
             return;
         }
-        cone_proj<float>(p0.h, p0.dual, p0.x, p0.eps, p0.w);
+        cone_flush_one(p0);
     }
-    if (cs.has_psd && ctx().psd_mode == 0 && ctx().psd_pairing) {
-        g_pending.h = h; g_pending.dual = dual; g_pending.x = x; g_pending.w = w; g_pending.eps = eps;
+    if ((cs.has_work || cs.has_psd) && ctx().psd_pairing) {
+        g_pending.h = h; g_pending.dual = dual; g_pending.dtype = DT<T>::id; g_pending.x = x; g_pending.w = w; g_pending.eps = (double)eps;
         g_cone_pending = true;                 // parked: runs with its partner, or alone as soon as anything else is called
         return;
     }
-    cone_proj<float>(h, dual, x, eps, w);
+    cone_proj<T>(h, dual, x, eps, w);
 }
 
 template <typename T> static void cone_group_min(tb_handle h, tb_view dp_tau) {
@@ -369,14 +389,17 @@ int tb_cone_destroy(tb_handle h) {
         ctx().cones[(size_t)h - 1] = nullptr;
     });
 }
-int tb_cone_proj_f32(tb_handle cone, int dual, tb_view x, float eps, tb_view w) { return api_keep_pending([&] { cone_proj_submit_f32(cone, dual, x, eps, w); }); }
+int tb_cone_proj_f32(tb_handle cone, int dual, tb_view x, float eps, tb_view w) { return api_keep_pending([&] { cone_proj_submit<float>(cone, dual, x, eps, w); }); }
 int tb_set_psd_pairing(int on) {
     return api([&] { ctx().psd_pairing = on != 0; });
 }
 int tb_psd_pairs(uint64_t* out) {
     return api_raw([&] { *out = ctx().psd_pairs; });
 }
-int tb_cone_proj_f64(tb_handle cone, int dual, tb_view x, double eps, tb_view w) { return api([&] { cone_proj<double>(cone, dual, x, eps, w); }); }
+int tb_cone_pairs(uint64_t* out) {
+    return api_raw([&] { *out = ctx().cone_pairs; });
+}
+int tb_cone_proj_f64(tb_handle cone, int dual, tb_view x, double eps, tb_view w) { return api_keep_pending([&] { cone_proj_submit<double>(cone, dual, x, eps, w); }); }
 int tb_cone_group_min_f32(tb_handle cone, tb_view t) { return api([&] { cone_group_min<float>(cone, t); }); }
 int tb_cone_group_min_f64(tb_handle cone, tb_view t) { return api([&] { cone_group_min<double>(cone, t); }); }
 }

@@ -179,6 +179,15 @@ char* dev_ptr(const tb_view& v, int dtype, bool write, bool full_overwrite) {
     return b.dev + v.off * b.esize;
 }
 
+bool host_scalar_if_current(const tb_view& x, int dtype, double* out) {
+    if (x.len != 1 || x.buf == 0) return false;
+    Buffer& b = get_buf(x.buf);
+    if (b.dtype != dtype || b.host == nullptr || x.off >= b.len) return false;
+    if (b.dev_newer.intersects(x.off, x.off + 1)) return false;
+    *out = dtype == TB_F32 ? (double)reinterpret_cast<const float*>(b.host)[x.off] : reinterpret_cast<const double*>(b.host)[x.off];
+    return true;
+}
+
 static tb_handle new_handle() {
     Context& c = ctx();
     if (!c.free_ids.empty()) {
@@ -276,6 +285,20 @@ template <typename T> static void get1(const tb_view& v, size_t idx, T* out) {
 template <typename T> static void set1(const tb_view& v, size_t idx, T val) {
     require_init();
     TB_REQUIRE(idx < v.len, "index out of range");
+    {
+        // The solver writes back what it has just read: tau := max(tau, 0), kappa := min(kappa, 0) (solver.rs:551-553, 566-568).
+        // When both copies of the element agree and already hold exactly this value the set changes nothing on either side:
+        // no launch, and - nothing on the device being touched - no speculation or prefetch is invalidated.
+        Buffer& b0 = get_buf(v.buf);
+        TB_REQUIRE(b0.dtype == DT<T>::id, "dtype mismatch");
+        TB_REQUIRE(v.off <= b0.len && v.len <= b0.len - v.off, "view out of range");
+        const size_t i = v.off + idx;
+        if (b0.host && b0.host_mut && !b0.dev_newer.intersects(i, i + 1) && !b0.host_newer.intersects(i, i + 1) &&
+            std::memcmp(b0.host + i * b0.esize, &val, sizeof(T)) == 0) {
+            ctx().sets_skipped += 1;
+            return;
+        }
+    }
     tb_view one{v.buf, v.off + idx, 1};
     T* p = wptr<T>(one, true);
     if (vp_enabled()) {

@@ -238,7 +238,7 @@ template <typename T, bool ABS>
 static void run_generic_t(const T* A, size_t lda, size_t n_row, size_t n_col, const T* x, T alpha, T beta, T* y) {
     Context& c = ctx();
     if (n_col == 0) return;
-    if (!ABS && n_col == 1 && n_row > 0 && vp_enabled(n_row)) {     // the transposed n x 1 operator: a dot product into y[0]
+    if (!ABS && n_col == 1 && n_row > 0 && vp_enabled_red(n_row)) {     // the transposed n x 1 operator: a dot product into y[0]
         vp_dot(DT<T>::id, (double)alpha, A, x, n_row, (double)beta, y);
         return;
     }
@@ -701,6 +701,15 @@ static void api_transform_ge(int transpose, size_t n_row, size_t n_col, T alpha,
             return;
         }
     }
+    if (!transpose && n_col == 1 && n_row > 0 && vp_enabled_wide(n_row)) {      // MatOp n x 1 applied to a host-current 1-element slice: see denseop_apply
+        double sv = 0.0;
+        if (host_scalar_if_current(x, DT<T>::id, &sv)) {
+            const T* A0 = rptr<T>(mat);
+            T* py0 = wptr<T>(y, beta == T(0));
+            vp_axs_imm(DT<T>::id, (double)alpha, A0, sv, (double)beta, py0, n_row);
+            return;
+        }
+    }
     const T* A = rptr<T>(mat);
     const T* px = rptr<T>(x);
     T* py = wptr<T>(y, beta == T(0));
@@ -745,6 +754,17 @@ template <typename T> static void denseop_apply(tb_handle h, int transpose, T al
         double v = 0.0;
         if (pf_try_dot(DT<T>::id, op.mat, x, y, (double)alpha, (double)beta, &v)) {
             set_scalar<T>(y, alpha * (T)v);          // served from the prefetched product: same arithmetic as the combine step it replaces
+            return;
+        }
+    }
+    if (!transpose && n == 1 && op.n_row == m && m > 0 && vp_enabled_wide(m)) {
+        // an m x 1 operator applied to a 1-element slice the host has just written (b and c on `work_one`, solver.rs:590-596): the
+        // scalar travels by value - no upload of the element, no device read of it, same arithmetic as the device-scalar form
+        double sv = 0.0;
+        if (host_scalar_if_current(x, DT<T>::id, &sv)) {
+            const T* A0 = rptr<T>(op.mat);
+            T* py0 = wptr<T>(y, beta == T(0));
+            vp_axs_imm(DT<T>::id, (double)alpha, A0, sv, (double)beta, py0, m);
             return;
         }
     }

@@ -92,7 +92,7 @@ __global__ void reduce_kernel(const T* __restrict__ x, size_t count, size_t inc,
 template <typename T, int MODE> static double reduce_sync(const T* x, size_t count, size_t inc) {
     Context& c = ctx();
     if (count == 0) return 0.0;
-    if (vp_enabled(count)) {      // the reduction closes the pending vector program and posts into the host box
+    if (vp_enabled_red(count)) {      // the reduction closes the pending vector program and posts into the host box
         const double r = vp_reduce_to_host(DT<T>::id, MODE, x, count, inc);
         dist_check_fault();
         return r;

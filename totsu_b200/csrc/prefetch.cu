@@ -19,6 +19,7 @@
 //     double like the vector-program reductions (results agree with the un-prefetched path to rounding, not bit for bit);
 //   * tb_set_scalar_prefetch(0) turns it off; tb_scalar_prefetch_stats reports kernels launched / requests served / dropped.
 #include "common.cuh"
+#include "vprog.cuh"
 #include <chrono>
 #include <cstdlib>
 
@@ -274,6 +275,44 @@ void pf_before_wait() {
     S.live = std::move(live);
     S.live_trigger = S.armed_trigger;
     S.live_seq = J.seq;
+    S.launched += 1;
+}
+
+// Called by the vector-program recorder just before it closes a program with a host-visible result (the trigger): the armed
+// reductions become micro-ops of that same program - partial sums on the cluster, combined into the prefetch slots of the host
+// box, sequence number last - so they cost neither a launch nor the two-stage kernel's latency chain, and the trigger's own value
+// is posted before them.  Falls back to pf_before_wait's kernel (armed list left alone) when a vector is too long for the cluster.
+void pf_into_program() {
+    PfState& S = g_pf;
+    static const bool ride = [] { const char* e = std::getenv("TB_PF_IN_PROGRAM"); return !(e && e[0] == '0'); }();      // A/B: 0 = always the separate kernel
+    if (S.armed.empty() || !S.on || !ride) return;
+    for (const PfReq& f : S.armed)
+        if (!vp_enabled_red(f.a.len)) return;
+    std::vector<PfReq> want;
+    want.swap(S.armed);
+    std::vector<PfLive> live;
+    int k = 0;
+    for (const PfReq& f : want) {
+        if (k >= kMaxJobs) break;
+        try {
+            if (f.a.len == 0 || (f.kind == 2 && f.a.len != f.b.len)) continue;
+            const void* a = dev_ptr(f.a, f.dtype, false);
+            const void* b = f.kind == 2 ? dev_ptr(f.b, f.dtype, false) : nullptr;
+            pf_log("ride", f);
+            vp_pf_reduce(f.dtype, f.kind, a, b, f.a.len, k);
+            live.push_back(PfLive{f, k, true});
+            ++k;
+        } catch (const Error&) {
+            pf_log("skip", f);
+            continue;
+        }
+    }
+    if (k == 0) return;
+    const uint64_t seq = ++S.seq_counter;
+    vp_pf_seq(seq);
+    S.live = std::move(live);
+    S.live_trigger = S.armed_trigger;
+    S.live_seq = seq;
     S.launched += 1;
 }
 

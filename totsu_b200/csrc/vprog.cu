@@ -42,6 +42,10 @@ constexpr int VP_MAX_CTAS = VP_CLUSTER;
 // tb_set_vprog_max_n / TB_VPROG_MAX_N change it (diagnostics).
 size_t g_vp_max_n = 49152;
 #define VP_MAX_N g_vp_max_n
+// Reductions (dot products, norms) are different: one pass of reads, no stores - 8 SMs take a 64 K-element dot in ~1.7 us, where
+// the dedicated two-stage kernel costs a launch plus ~8 us of its own latency chain.  They stay on the cluster up to 512 K elements
+// and never make a program wide.
+constexpr size_t VP_MAX_N_RED = size_t(1) << 19;
 constexpr size_t VP_WIDE_MAX_N = size_t(1) << 22;    // beyond this a dedicated kernel with a larger grid is the better tool
 
 enum : uint8_t {
@@ -58,6 +62,8 @@ enum : uint8_t {
     VOP_PART_SUMSQ,      // slot[rank] = sum x[i*inc]^2                             aux = slot, aux2 = inc
     VOP_PART_ABSSUM,     // slot[rank] = sum |x[i*inc]|
     VOP_COMBINE_Y,       // y[0] = a * sum_r slot[r] (+ b * y[0])                   aux = slot
+    VOP_COMBINE_PF,      // box[4 + aux2] = sum_r slot[r]  (scalar prefetch, prefetch.cu)       aux = slot, aux2 = prefetch slot
+    VOP_PF_SEQ,          // box[8] = aux2 after a system fence: the prefetched values of this program are complete
     VOP_COMBINE_BOX,     // box <- sum_r slot[r]                                    aux = slot, seq in aux2
     VOP_FETCH_BOX,       // box <- x[0]                                             seq in aux2
 };
@@ -138,7 +144,7 @@ template <typename T> __device__ __forceinline__ void run_elementwise(const Micr
             break;
         }
         case VOP_AXS: {
-            const T sc = ldg_cg(d);
+            const T sc = op.aux ? (T)__longlong_as_double((long long)op.aux2) : ldg_cg(d);      // aux = 1: the scalar travels by value
             if (op.mode == 0) { for (size_t i = gtid; i < n; i += gstride) y[i] = a * (ldg_cg(x + i) * sc); }
             else { for (size_t i = gtid; i < n; i += gstride) y[i] = a * (ldg_cg(x + i) * sc) + b * ldg_cg(y + i); }
             break;
@@ -212,6 +218,18 @@ __device__ __forceinline__ void run_program(const Program& prog) {
                     }
                 }
                 break;
+            case VOP_COMBINE_PF:
+                if (rank == 0 && threadIdx.x < 32) {
+                    const double s = combine_slot(prog.slots + (size_t)op.aux * VP_MAX_CTAS, g);
+                    if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(prog.box + 4 + op.aux2) = s;
+                }
+                break;
+            case VOP_PF_SEQ:
+                if (rank == 0 && threadIdx.x == 0) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned long long*>(prog.box + 8) = op.aux2;
+                }
+                break;
             case VOP_COMBINE_BOX:
                 if (rank == 0 && threadIdx.x < 32) {
                     const double s = combine_slot(prog.slots + (size_t)op.aux * VP_MAX_CTAS, g);
@@ -276,7 +294,7 @@ inline Range elems_of(const void* p, size_t bytes) { return Range{reinterpret_ca
 void push(MicroOp op, std::initializer_list<Range> rd, std::initializer_list<Range> wr, bool reduction = false) {
     Recorder& R = g_rec;
     if (R.prog.n_ops == VP_MAX_OPS) vp_flush();
-    const bool big = (size_t)op.n > VP_MAX_N;
+    const bool big = !reduction && (size_t)op.n > VP_MAX_N;
     if (R.prog.n_ops > 0) {
         // a wide program has neither barriers nor reductions (their partial slots are sized for the cluster)
         if (big && !R.wide && (R.has_barrier || R.has_reduction)) vp_flush();
@@ -308,6 +326,7 @@ Range slot_range(int slot) { return range_of(g_rec.slots + (size_t)slot * VP_MAX
 
 bool vp_enabled(size_t n) { return ctx().vprog && n <= VP_MAX_N; }
 void vp_set_max_n(size_t n) { vp_flush(); g_vp_max_n = n; }
+bool vp_enabled_red(size_t n) { return ctx().vprog && n <= VP_MAX_N_RED; }
 // element-wise ops of any practical length can be recorded: beyond VP_MAX_N the program becomes a barrier-free "wide" one
 bool vp_enabled_wide(size_t n) { return ctx().vprog && n <= VP_WIDE_MAX_N; }
 
@@ -408,6 +427,14 @@ void vp_axs(int dtype, double a, const void* x, const void* s, double b, void* y
     if (op.mode == 0) push(op, {elems_of(x, n * es(dtype)), range_of(s, es(dtype))}, {ry});
     else push(op, {elems_of(x, n * es(dtype)), range_of(s, es(dtype)), ry}, {ry});
 }
+void vp_axs_imm(int dtype, double a, const void* x, double sval, double b, void* y, size_t n) {
+    MicroOp op = mk(VOP_AXS, dtype); op.x = x; op.p2 = nullptr; op.y = y; op.a = a; op.b = b; op.n = n; op.mode = b == 0.0 ? 0 : 2;
+    op.aux = 1;
+    std::memcpy(&op.aux2, &sval, sizeof(double));
+    const Range ry = elems_of(y, n * es(dtype));
+    if (op.mode == 0) push(op, {elems_of(x, n * es(dtype))}, {ry});
+    else push(op, {elems_of(x, n * es(dtype)), ry}, {ry});
+}
 void vp_set1(int dtype, void* y, double v) {
     MicroOp op = mk(VOP_SET1, dtype); op.y = y; op.a = v; op.n = 1;
     push(op, {}, {range_of(y, es(dtype))});
@@ -428,13 +455,29 @@ double vp_reduce_to_host(int dtype, int mode, const void* x, size_t count, size_
     const uint64_t seq = box_next();
     MicroOp q = mk(VOP_COMBINE_BOX, dtype); q.aux = (uint32_t)slot; q.aux2 = seq;
     push(q, {slot_range(slot)}, {}, true);
+    pf_into_program();            // reductions predicted to be asked for next ride in this same launch (prefetch.cu)
     vp_flush();
     return box_wait(seq);
+}
+// scalar prefetch riding in the pending program: one reduction whose result goes to prefetch slot k of the host box
+// (kind 1: sum of squares of a, 2: dot(a, b)); vp_pf_seq closes the set.  Accumulation in double, fixed order.
+void vp_pf_reduce(int dtype, int kind, const void* a, const void* b, size_t n, int k) {
+    const int slot = take_slot();
+    MicroOp p = mk(kind == 2 ? VOP_PART_DOT : VOP_PART_SUMSQ, dtype); p.x = a; p.p2 = b; p.n = n; p.aux = (uint32_t)slot; p.aux2 = 1;
+    if (kind == 2) push(p, {range_of(a, n * es(dtype)), range_of(b, n * es(dtype))}, {slot_range(slot)}, true);
+    else push(p, {range_of(a, n * es(dtype))}, {slot_range(slot)}, true);
+    MicroOp q = mk(VOP_COMBINE_PF, dtype); q.aux = (uint32_t)slot; q.aux2 = (unsigned long long)k; q.n = 1;
+    push(q, {slot_range(slot)}, {range_of(ctx().hostbox_dev + 4 + k, sizeof(double))}, true);
+}
+void vp_pf_seq(unsigned long long seq) {
+    MicroOp q = mk(VOP_PF_SEQ, TB_F64); q.aux2 = seq; q.n = 1;
+    push(q, {}, {range_of(ctx().hostbox_dev + 8, sizeof(double))}, true);
 }
 double vp_fetch_to_host(int dtype, const void* x) {
     const uint64_t seq = box_next();
     MicroOp q = mk(VOP_FETCH_BOX, dtype); q.x = x; q.aux2 = seq;
     push(q, {range_of(x, es(dtype))}, {});
+    pf_into_program();
     vp_flush();
     return box_wait(seq);
 }
