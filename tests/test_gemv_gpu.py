@@ -195,6 +195,52 @@ def test_denseop_apply_pair_absadd(dt, shape):
     capi.check(L.tb_denseop_destroy(h.value))
     abuf.release()
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("m", [7, 4097, 70000])
+def test_column_operator_on_a_host_written_scalar(dt, m):
+    """An m x 1 operator (the solver's b and c) applied to a 1-element slice the host has just written (`work_one = [1]`,
+    solver.rs:590-596): the scalar travels by value - no upload kernel - and the result is bit-identical to the same apply with
+    the scalar on the device; both through tb_denseop_apply and through MatOp's tb_transform_ge."""
+    L = capi.lib()
+    rng = np.random.default_rng(m)
+    col = rng.standard_normal(m).astype(dt)
+    y0 = rng.standard_normal(m).astype(dt)
+    cbuf, cv = device_matrix(np.asfortranarray(col.reshape(m, 1)))
+    h = C.c_int64()
+    capi.check(L.tb_denseop_create(capi.dtype_id(dt), cv, m, 1, 0, 0, C.byref(h)))
+    alpha, beta, sval = dt(-0.75), dt(0.5), dt(1.25)
+    want = (alpha * (col * sval) + beta * y0).astype(dt)                      # the arithmetic of both forms
+
+    def launches():
+        capi.check(L.tb_flush())
+        n = C.c_uint64(); capi.check(L.tb_launch_count(C.byref(n)))
+        return n.value
+    res = {}
+    for where in ("host", "device"):
+        for api in ("denseop", "transform_ge"):
+            s1 = np.array([sval], dtype=dt)
+            sb = capi.Buf(s1)
+            if where == "device":
+                capi.check(capi.fn("tb_scale", dt)(1.0, sb.view()))           # the device copy is now the newer one
+            y = y0.copy()
+            yb = capi.Buf(y)
+            capi.check(capi.fn("tb_scale", dt)(1.0, yb.view()))               # y on the device already
+            l0 = launches()
+            if api == "denseop":
+                capi.check(capi.fn("tb_denseop_apply", dt)(h.value, 0, alpha, sb.view(), beta, yb.view()))
+            else:
+                capi.check(capi.fn("tb_transform_ge", dt)(0, m, 1, alpha, cv, sb.view(), beta, yb.view()))
+            n_l = launches() - l0
+            yb.release(); sb.release()
+            res[(where, api)] = (y, n_l)
+            assert rel_linf(y, want.astype(np.float64)) <= (1e-6 if dt == np.float32 else 1e-15), (where, api)   # the device contracts to FMA
+    for api in ("denseop", "transform_ge"):
+        assert np.array_equal(res[("host", api)][0], res[("device", api)][0]), api        # same arithmetic, bit for bit
+    # by value: one launch (the program with the apply); from a host-newer device scalar the upload kernel would come on top
+    assert res[("host", "denseop")][1] == 1 and res[("host", "transform_ge")][1] == 1, {k: v[1] for k, v in res.items()}
+    capi.check(L.tb_denseop_destroy(h.value))
+    cbuf.release()
+
 
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("shape", [(2048, 640), (5000, 333), (1028, 2050)])

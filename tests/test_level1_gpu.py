@@ -110,6 +110,41 @@ def test_coherence_get_set_host_views(dt):
     want[4] = 101; want[8] = 0
     assert np.array_equal(host, want.astype(dt))
 
+@pytest.mark.parametrize("dt", DTYPES)
+def test_set_of_the_value_just_read_launches_nothing(dt):
+    """The solver writes back what it has just read - tau := max(tau, 0), kappa := min(kappa, 0) (solver.rs:551-553, 566-568).
+    A set of exactly the value both copies hold is a no-op (no launch); a different value, or an element whose device copy is
+    newer than the host's, still goes through; +0.0 over -0.0 is a change."""
+    L = capi.lib()
+    F = C.c_float if dt == np.float32 else C.c_double
+    host = np.arange(1, 9, dtype=dt)
+    buf = capi.Buf(host)
+    v = buf.view()
+    out = F()
+    get, set1 = capi.fn("tb_get1", dt), capi.fn("tb_set1", dt)
+    capi.check(capi.fn("tb_scale", dt)(-3.0, v))                         # device-newer: [-3, -6, ...]
+    capi.check(get(v, 2, C.byref(out))); assert out.value == -9         # round trip; both copies of element 2 agree now
+
+    def launches():
+        capi.check(L.tb_flush())
+        n = C.c_uint64(); capi.check(L.tb_launch_count(C.byref(n)))
+        return n.value
+    l0 = launches()
+    capi.check(set1(v, 2, -9.0))                                         # kappa := min(kappa, 0) with kappa < 0
+    assert launches() == l0
+    capi.check(set1(v, 2, 0.0))                                          # a real change
+    l1 = launches()
+    assert l1 == l0 + 1
+    capi.check(get(v, 2, C.byref(out))); assert out.value == 0 and launches() == l1      # write-through: no round trip
+    capi.check(set1(v, 2, -0.0))                                         # bitwise different from +0.0
+    assert launches() == l1 + 1
+    capi.check(set1(v, 3, -12.0))                                        # equal to the device value, but the host copy is stale: not skipped
+    assert launches() == l1 + 2
+    buf.release()
+    want = np.arange(1, 9, dtype=np.float64) * -3
+    want[2] = -0.0
+    assert np.array_equal(host, want.astype(dt)) and np.signbit(host[2])
+
 
 def test_length_mismatch_is_an_error():
     """f64lapack.rs:27,39,63-64 assert; the C ABI returns TB_ERR_ARG and the shim asserts."""
