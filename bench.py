@@ -743,10 +743,11 @@ def main():
             "vector_programs": {"enabled": bool(args.vprog), "launches_per_iteration": cnt[1] / steps,
                                 "micro_ops_per_iteration": cnt[2] / steps,
                                 "note": "small vector commands recorded into one cluster launch per batch (csrc/vprog.cu); each program counts as one of gpu_launches"},
-            "scalar_prefetch": {"enabled": bool(args.scalar_prefetch), "prefetch_kernels_per_iteration": cnt[6] / steps, "scalars_served_without_a_round_trip_per_iteration": cnt[7] / steps,
+            "scalar_prefetch": {"enabled": bool(args.scalar_prefetch), "prefetch_batches_per_iteration": cnt[6] / steps, "scalars_served_without_a_round_trip_per_iteration": cnt[7] / steps,
                                 "dropped": int(cnt[8]),
-                                "note": "g_x, g_y and |d| of criteria_conv (solver.rs:599-608) are computed behind the kappa / |p| round trips and served from the "
-                                        "mapped host box: 6 host round trips per iteration become 3"},
+                                "note": "g_x, g_y and |d| of criteria_conv (solver.rs:599-608) are computed behind the kappa / |p| round trips - as extra micro-ops of the "
+                                        "program that posts kappa / |p| (no launch of their own; a separate small kernel when a vector is too long for the cluster "
+                                        "executor) - and served from the mapped host box: 6 host round trips per iteration become 3"},
             "programmatic_dependent_launch": bool(args.pdl),
             "host": {"loop_s": win_host[med], "waiting_for_device_s": win_wait[med], "host_visible_scalars_per_iteration": win_scalars[med] / steps,
                      "note": "host time of the median window's loop and the part of it spent spinning on device results: the rest is issuing launches"},
