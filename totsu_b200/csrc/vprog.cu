@@ -291,10 +291,10 @@ inline Range range_of(const void* p, size_t bytes) { return Range{reinterpret_ca
 inline Range elems_of(const void* p, size_t bytes) { return Range{reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p) + bytes, true}; }
 
 // Append one micro-op; rd[] / wr[] are the byte ranges it reads / writes.
-void push(MicroOp op, std::initializer_list<Range> rd, std::initializer_list<Range> wr, bool reduction = false) {
+void push(MicroOp op, std::initializer_list<Range> rd, std::initializer_list<Range> wr, bool reduction = false, bool force_big = false) {
     Recorder& R = g_rec;
     if (R.prog.n_ops == VP_MAX_OPS) vp_flush();
-    const bool big = !reduction && (size_t)op.n > VP_MAX_N;
+    const bool big = !reduction && ((size_t)op.n > VP_MAX_N || force_big);
     if (R.prog.n_ops > 0) {
         // a wide program has neither barriers nor reductions (their partial slots are sized for the cluster)
         if (big && !R.wide && (R.has_barrier || R.has_reduction)) vp_flush();
@@ -418,8 +418,13 @@ void vp_finalize(int dtype, const void* part, int nparts, size_t ld, size_t len,
     MicroOp op = mk(VOP_FINALIZE, dtype); op.x = part; op.y = y; op.a = a; op.b = b; op.n = len; op.aux = (uint32_t)nparts; op.aux2 = ld;
     op.mode = b == 0.0 ? 0 : 2;
     const Range rp = range_of(part, ((size_t)(nparts - 1) * ld + len) * es(dtype)), ry = elems_of(y, len * es(dtype));
-    if (op.mode == 0) push(op, {rp}, {ry});
-    else push(op, {rp, ry}, {ry});
+    // What a finalize moves is nparts x len partials, not len: C2's 17 412 outputs sum 74 partials each - 5.2 MB, 13 us through the 8
+    // SMs of the cluster (~0.4 TB/s) against ~2 us on the whole chip plus a launch boundary.  Beyond 512 K partial elements (2 MB: where the cluster time passes the cost of a launch boundary) the op
+    // counts as long and goes to a wide program.  TB_VP_FINALIZE_WIDE (elements) moves the threshold (diagnostics).
+    static const size_t wide_elems = [] { const char* e = std::getenv("TB_VP_FINALIZE_WIDE"); return e ? (size_t)std::atoll(e) : (size_t)524288; }();
+    const bool long_op = (size_t)nparts * len > wide_elems;
+    if (op.mode == 0) push(op, {rp}, {ry}, false, long_op);
+    else push(op, {rp, ry}, {ry}, false, long_op);
 }
 void vp_axs(int dtype, double a, const void* x, const void* s, double b, void* y, size_t n) {
     MicroOp op = mk(VOP_AXS, dtype); op.x = x; op.p2 = s; op.y = y; op.a = a; op.b = b; op.n = n; op.mode = b == 0.0 ? 0 : 2;
